@@ -1,0 +1,33 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE — builds the UNMODIFIED miniAero reference sources, where they lie under
+# /root/reference/kokkos, against the Kokkos stand-in in oracle/kokkos_standin/ (Kokkos itself is
+# not vendored by the reference and not installed; see DESIGN.md "Oracle").  Outputs go to
+# oracle/_ref/ only (git-ignored, but shipped to the GPU box by gpurun).  No reference source is
+# copied into this repository.
+#
+#   miniAero.cell        -DCELL_FLUX      serial    : the parity oracle (deterministic slot-ordered gather)
+#   miniAero.cell.omp    -DCELL_FLUX      -fopenmp  : CPU baseline ("reference source on an OpenMP loop")
+#   miniAero.atomics     -DATOMICS_FLUX   serial    : the reference Makefile's default build (noise floor)
+#   miniAero.atomics.omp -DATOMICS_FLUX   -fopenmp
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${MINIAERO_REFERENCE:-/root/reference/kokkos}"
+OUT="$HERE/_ref"
+if [ ! -f "$REF/Main.C" ]; then
+  echo "build_ref.sh: reference sources not found at $REF (skipping; prebuilt $OUT is used if present)"
+  exit 0
+fi
+mkdir -p "$OUT"
+SRCS="Main.C Parallel3DMesh.C MeshProcessor.C Face.C Cell.C ElementTopo.C ElementTopoHexa8.C CopyGhost.C MemoryUsage.C"
+# -ffp-contract=off: plain IEEE-754 evaluation in source order (no FMA contraction), the oracle's definition.
+COMMON="-O3 -std=gnu++17 -w -ffp-contract=off -I$HERE/kokkos_standin -I$REF"
+build() { # name, flags
+  local name="$1"; shift
+  if [ "$OUT/$name" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] && [ "$OUT/$name" -nt "$HERE/build_ref.sh" ]; then return; fi
+  (cd "$REF" && g++ $COMMON "$@" $SRCS -o "$OUT/$name")
+  echo "built $OUT/$name"
+}
+build miniAero.cell        -DCELL_FLUX
+build miniAero.cell.omp    -DCELL_FLUX -fopenmp
+build miniAero.atomics     -DATOMICS_FLUX
+build miniAero.atomics.omp -DATOMICS_FLUX -fopenmp
