@@ -1,0 +1,66 @@
+// Launch interface of the CUDA kernels (kernels.cu is compiled twice: namespace ma_fast with FMA
+// contraction, namespace ma_strict with -fmad=false; the solver picks one per ma_arith).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace ma {
+
+struct TileInfoDev {
+  int cell_start, cell_count, face_start, face_count;
+};
+
+// Device mesh in the tile-packed structure-of-arrays layout (see DESIGN.md "Data layout in HBM").
+struct DevMesh {
+  int n_owned, n_cells, stride;        // cells; SoA component stride
+  int n_tiles, slot_stride;
+  long n_tile_faces;                   // component stride of face_geom
+  int flux_smem_stride;                // per-component stride of the shared-memory flux staging
+  const TileInfoDev *tiles;
+  const double *cell_xyz;              // [3][stride]
+  const double *cell_vol;              // [stride]
+  const uint16_t *slot_face;           // [6][slot_stride]
+  const double *face_geom;             // [12][n_tile_faces]: normal, tangent, binormal, centroid
+  const int *face_left, *face_right;   // [n_tile_faces]
+  double inflow[5];                    // TimeSolverExplicitRK4.h:218-223
+};
+
+struct StageArgs {
+  const double *W;     // stage state, read for every cell a tile touches   ("solution_temp")
+  const double *Un;    // state at the start of the step                     ("solution_n")
+  const double *AccIn; // running RK sum                                     ("solution_np1")
+  double *AccOut;
+  double *Wnext;       // next stage state; for the last stage the new Un
+  const double *grad;  // [15][stride]
+  const double *lim;   // [5][stride]
+  double dt, alpha_next, beta;
+  int kind;            // 0 first stage (W == Un == Acc), 1 middle, 2 last
+};
+
+}  // namespace ma
+
+#define MA_DECLARE_KERNEL_API(NS)                                                                                    \
+  namespace NS {                                                                                                     \
+  /* GreenGauss.h:51-270 + StencilLimiter.h:56-500 fused, cell-centric, tiles [tile_begin, tile_begin+ntiles) */     \
+  cudaError_t launch_grad_limiter(const ma::DevMesh &m, const double *W, double *grad, double *lim, bool second,     \
+                                  int tile_begin, int ntiles, int threads, cudaStream_t st);                         \
+  /* Flux.h:52-229 + the four *_BC.h + TimeSolverExplicitRK4.h:106-128 fused */                                      \
+  cudaError_t launch_flux_rk(const ma::DevMesh &m, const ma::StageArgs &a, bool second, bool viscous,                \
+                             int tile_begin, int ntiles, int threads, cudaStream_t st);                              \
+  cudaError_t flux_rk_prepare(int smem_bytes);                                                                       \
+  /* Initial_Conditions.h:38-133 */                                                                                  \
+  cudaError_t launch_initial_conditions(const ma::DevMesh &m, double *Un, int problem_type, double midx,             \
+                                        cudaStream_t st);                                                            \
+  cudaError_t probe_roe(int n, const double *vl, const double *vr, const double *nn, const double *tt,               \
+                        const double *bb, double *flux, cudaStream_t st);                                            \
+  cudaError_t probe_viscous(int n, const double *g, const double *v, const double *a, double *vf, cudaStream_t st);  \
+  cudaError_t probe_primitives(int n, const double *u, double *v, cudaStream_t st);                                  \
+  cudaError_t probe_venkat(int n, const double *dmax, const double *dmin, const double *du, const double *dx3,       \
+                           double *phi, cudaStream_t st);                                                            \
+  cudaError_t probe_vanalbada(int n, const double *dmax, const double *dmin, const double *du, double *phi,          \
+                              cudaStream_t st);                                                                      \
+  }
+
+MA_DECLARE_KERNEL_API(ma_fast)
+MA_DECLARE_KERNEL_API(ma_strict)

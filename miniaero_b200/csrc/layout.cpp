@@ -1,0 +1,377 @@
+// See layout.h.  Everything here is one-time host setup (the analogue of the reference's
+// copy_faces / copy_cell_data, Faces.h:88-145, Cells.h:126-146); it is O(cells) and OpenMP-parallel.
+#include "layout.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#ifdef _OPENMP
+#include <omp.h>
+#include <parallel/algorithm>
+#endif
+
+#include "host_common.h"
+
+namespace ma {
+
+namespace {
+
+struct FaceSrc {  // where global face g lives in the caller's arrays
+  const ma_faces *f;
+  int index;
+  int bc_type;  // -1: internal
+};
+
+inline int round_up(long v, int m) { return (int)(((v + m - 1) / m) * m); }
+
+}  // namespace
+
+int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], HostLayout &L) {
+  const int n_owned = mesh.num_owned_cells, n_ghost = mesh.num_ghosts;
+  const long n_cells = (long)n_owned + n_ghost;
+  if (n_owned <= 0 || n_ghost < 0) return ma_set_error(MA_ERR_INVALID, "mesh: num_owned_cells must be > 0");
+  if (!mesh.cell_coordinates || !mesh.cell_volumes)
+    return ma_set_error(MA_ERR_INVALID, "mesh: cell_coordinates / cell_volumes are NULL");
+  if (mesh.num_boundary_sets < 0 || mesh.num_boundary_sets > MA_MAX_BC_SETS)
+    return ma_set_error(MA_ERR_INVALID, "mesh: num_boundary_sets out of range");
+  auto faces_ok = [](const ma_faces &f) {
+    return f.nfaces == 0 || (f.nfaces > 0 && f.coordinates && f.face_normal && f.face_tangent && f.face_binormal &&
+                             f.face_cell_conn && f.cell_flux_index);
+  };
+  if (!faces_ok(mesh.internal_faces)) return ma_set_error(MA_ERR_INVALID, "mesh: internal_faces has NULL arrays");
+  for (int b = 0; b < mesh.num_boundary_sets; ++b) {
+    if (!faces_ok(mesh.boundary_faces[b])) return ma_set_error(MA_ERR_INVALID, "mesh: boundary set has NULL arrays");
+    if (mesh.boundary_type[b] < 0 || mesh.boundary_type[b] > 3)
+      return ma_set_error(MA_ERR_INVALID, "mesh: unknown boundary_type");
+  }
+  if (n_ghost > 0 && (mesh.num_ranks < 2 || !mesh.send_count || !mesh.recv_count || !mesh.send_local_ids ||
+                      !mesh.recv_local_ids))
+    return ma_set_error(MA_ERR_INVALID, "mesh: ghosts present but exchange lists are missing");
+
+  L = HostLayout();
+  L.n_owned = n_owned;
+  L.n_ghost = n_ghost;
+  L.stride = round_up(n_cells, 32);
+  for (int d = 0; d < 3; ++d) L.tile_dims[d] = tile_dims_in[d] > 0 ? tile_dims_in[d] : 8;
+  L.max_tile_cells = L.tile_dims[0] * L.tile_dims[1] * L.tile_dims[2];
+  if (L.max_tile_cells > 4096) return ma_set_error(MA_ERR_INVALID, "tile_dims: at most 4096 cells per tile");
+
+  // ---- 1. cell -> face table over owned cells: ref = global_face*2 + side, global face numbering is
+  // internal faces first, then the boundary sets in order.
+  const long n_int = mesh.internal_faces.nfaces;
+  std::vector<long> set_base(mesh.num_boundary_sets + 1, n_int);
+  for (int b = 0; b < mesh.num_boundary_sets; ++b) set_base[b + 1] = set_base[b] + mesh.boundary_faces[b].nfaces;
+  const long n_faces_all = set_base[mesh.num_boundary_sets];
+  if (n_faces_all >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "mesh: more than 2^31 faces");
+  const uint32_t kNone = 0xFFFFFFFFu;
+  std::vector<uint32_t> cf((size_t)n_owned * 6, kNone);
+  int bad = 0;
+  {
+    const int *conn = mesh.internal_faces.face_cell_conn, *slot = mesh.internal_faces.cell_flux_index;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long f = 0; f < n_int; ++f) {
+      for (int side = 0; side < 2; ++side) {
+        const int c = conn[2 * f + side], s = slot[2 * f + side];
+        if (c < 0 || c >= n_cells || s < 0 || s > 5) {
+          ++bad;
+          continue;
+        }
+        if (c < n_owned) cf[(size_t)c * 6 + s] = (uint32_t)(f * 2 + side);
+      }
+    }
+    for (int b = 0; b < mesh.num_boundary_sets; ++b) {
+      const ma_faces &F = mesh.boundary_faces[b];
+      const long base = set_base[b];
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+      for (long f = 0; f < F.nfaces; ++f) {
+        const int c = F.face_cell_conn[2 * f], s = F.cell_flux_index[2 * f];
+        if (c < 0 || c >= n_owned || s < 0 || s > 5) {
+          ++bad;
+          continue;
+        }
+        cf[(size_t)c * 6 + s] = (uint32_t)((base + f) * 2);
+      }
+    }
+  }
+  if (bad) return ma_set_error(MA_ERR_INVALID, "mesh: face_cell_conn / cell_flux_index out of range");
+  {
+    long missing = 0;
+#pragma omp parallel for schedule(static) reduction(+ : missing)
+    for (long i = 0; i < (long)n_owned * 6; ++i) missing += (cf[i] == kNone);
+    if (missing)
+      return ma_set_error(MA_ERR_INVALID, "mesh: " + std::to_string(missing) +
+                                              " (cell, slot) pairs of owned cells have no face (hex cells need 6)");
+  }
+  auto face_src = [&](uint32_t ref) {
+    const long g = ref >> 1;
+    FaceSrc s;
+    if (g < n_int) {
+      s.f = &mesh.internal_faces, s.index = (int)g, s.bc_type = -1;
+    } else {
+      int b = 0;
+      while (g >= set_base[b + 1]) ++b;
+      s.f = &mesh.boundary_faces[b], s.index = (int)(g - set_base[b]), s.bc_type = mesh.boundary_type[b];
+    }
+    return s;
+  };
+  // the cell on the other side of (owned) cell c's face `ref`; -1 for a boundary face
+  auto other_cell = [&](uint32_t ref) -> int {
+    const long g = ref >> 1;
+    if (g >= n_int) return -1;
+    return mesh.internal_faces.face_cell_conn[2 * g + (1 - (int)(ref & 1))];
+  };
+
+  // ---- 2. spatial binning of owned cells.  The mean centroid spacing along each axis is taken over
+  // internal faces whose cell-to-cell vector is dominated by that axis; for a structured block this
+  // recovers (i,j,k) exactly, for a general hex mesh it only has to give compact tiles.
+  const double *xc = mesh.cell_coordinates;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (long c = 0; c < n_owned; ++c)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], xc[3 * c + d]);
+      hi[d] = std::max(hi[d], xc[3 * c + d]);
+    }
+  double hsum[3] = {0, 0, 0};
+  long hcnt[3] = {0, 0, 0};
+  {
+    const int *conn = mesh.internal_faces.face_cell_conn;
+    double s0 = 0, s1 = 0, s2 = 0;
+    long c0 = 0, c1 = 0, c2 = 0;
+#pragma omp parallel for schedule(static) reduction(+ : s0, s1, s2, c0, c1, c2)
+    for (long f = 0; f < n_int; ++f) {
+      const int l = conn[2 * f], r = conn[2 * f + 1];
+      if (l >= n_owned || r >= n_owned) continue;
+      const double d0 = std::fabs(xc[3 * (long)r] - xc[3 * (long)l]);
+      const double d1 = std::fabs(xc[3 * (long)r + 1] - xc[3 * (long)l + 1]);
+      const double d2 = std::fabs(xc[3 * (long)r + 2] - xc[3 * (long)l + 2]);
+      if (d0 >= d1 && d0 >= d2) {
+        s0 += d0, ++c0;
+      } else if (d1 >= d2) {
+        s1 += d1, ++c1;
+      } else {
+        s2 += d2, ++c2;
+      }
+    }
+    hsum[0] = s0, hsum[1] = s1, hsum[2] = s2;
+    hcnt[0] = c0, hcnt[1] = c1, hcnt[2] = c2;
+  }
+  double h[3];
+  long nbin[3];
+  for (int d = 0; d < 3; ++d) {
+    h[d] = hcnt[d] ? hsum[d] / (double)hcnt[d] : 0.0;
+    if (!(h[d] > 0.0) || !((hi[d] - lo[d]) / h[d] < 1e9)) h[d] = (hi[d] - lo[d]) + 1.0;  // one bin
+    nbin[d] = (long)std::floor((hi[d] - lo[d]) / h[d] + 0.5) + 1;
+  }
+  long ntile_d[3];
+  for (int d = 0; d < 3; ++d) ntile_d[d] = (nbin[d] + L.tile_dims[d] - 1) / L.tile_dims[d];
+
+  struct Key {
+    uint64_t tile;
+    uint32_t local;
+    int cell;
+  };
+  std::vector<Key> keys((size_t)n_owned);
+#pragma omp parallel for schedule(static)
+  for (long c = 0; c < n_owned; ++c) {
+    long q[3], t[3], l[3];
+    for (int d = 0; d < 3; ++d) {
+      q[d] = (long)std::floor((xc[3 * c + d] - lo[d]) / h[d] + 0.5);
+      q[d] = std::max(0L, std::min(q[d], nbin[d] - 1));
+      t[d] = q[d] / L.tile_dims[d];
+      l[d] = q[d] % L.tile_dims[d];
+    }
+    keys[c].tile = ((uint64_t)t[0] * ntile_d[1] + t[1]) * ntile_d[2] + t[2];
+    keys[c].local = (uint32_t)((l[0] * L.tile_dims[1] + l[1]) * L.tile_dims[2] + l[2]);
+    keys[c].cell = (int)c;
+  }
+  auto key_less = [](const Key &a, const Key &b) {
+    if (a.tile != b.tile) return a.tile < b.tile;
+    if (a.local != b.local) return a.local < b.local;
+    return a.cell < b.cell;
+  };
+#ifdef _OPENMP
+  __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+#else
+  std::sort(keys.begin(), keys.end(), key_less);
+#endif
+
+  // ---- 3. cut tiles, classify (touches a ghost?), order interior tiles first, renumber
+  struct RawTile {
+    long first;
+    int count;
+    int boundary;
+  };
+  std::vector<RawTile> raw;
+  raw.reserve((size_t)n_owned / std::max(1, L.max_tile_cells / 2) + 16);
+  for (long i = 0; i < n_owned;) {
+    long j = i + 1;
+    while (j < n_owned && keys[j].tile == keys[i].tile && (j - i) < L.max_tile_cells) ++j;
+    raw.push_back({i, (int)(j - i), 0});
+    i = j;
+  }
+  const long n_tiles = (long)raw.size();
+  if (n_ghost > 0) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long t = 0; t < n_tiles; ++t) {
+      int bnd = 0;
+      for (long i = raw[t].first; i < raw[t].first + raw[t].count && !bnd; ++i) {
+        const int c = keys[i].cell;
+        for (int s = 0; s < 6; ++s)
+          if (other_cell(cf[(size_t)c * 6 + s]) >= n_owned) {
+            bnd = 1;
+            break;
+          }
+      }
+      raw[t].boundary = bnd;
+    }
+  }
+  std::vector<long> order;
+  order.reserve(n_tiles);
+  for (long t = 0; t < n_tiles; ++t)
+    if (!raw[t].boundary) order.push_back(t);
+  L.n_interior_tiles = (int)order.size();
+  for (long t = 0; t < n_tiles; ++t)
+    if (raw[t].boundary) order.push_back(t);
+  L.n_tiles = (int)n_tiles;
+  L.tiles.resize(n_tiles);
+  L.new2old.resize(n_cells);
+  L.old2new.resize(n_cells);
+  {
+    long next = 0;
+    for (long k = 0; k < n_tiles; ++k) {
+      L.tiles[k].cell_start = (int)next;
+      L.tiles[k].cell_count = raw[order[k]].count;
+      next += raw[order[k]].count;
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long k = 0; k < n_tiles; ++k) {
+      const RawTile &r = raw[order[k]];
+      for (int i = 0; i < r.count; ++i) {
+        const int oldc = keys[r.first + i].cell;
+        const int newc = L.tiles[k].cell_start + i;
+        L.new2old[newc] = oldc;
+        L.old2new[oldc] = newc;
+      }
+    }
+    for (long g = n_owned; g < n_cells; ++g) L.new2old[g] = (int)g, L.old2new[g] = (int)g;
+  }
+  std::vector<Key>().swap(keys);
+
+  // ---- 4. cell SoA
+  L.cell_xyz.assign((size_t)3 * L.stride, 0.0);
+  L.cell_vol.assign((size_t)L.stride, 1.0);
+#pragma omp parallel for schedule(static)
+  for (long c = 0; c < n_cells; ++c) {
+    const long o = L.new2old[c];
+    for (int d = 0; d < 3; ++d) L.cell_xyz[(size_t)d * L.stride + c] = xc[3 * o + d];
+    L.cell_vol[c] = mesh.cell_volumes[o];
+  }
+
+  // ---- 5. tile face lists.  A face is emitted by its in-tile cell with the larger tile-local index
+  // (or by its only in-tile cell), in (cell, slot) order: the flux sweep then walks cells in order
+  // and every cell's data is touched within a short window.
+  L.slot_stride = round_up(n_owned, 32);
+  L.slot_face.assign((size_t)6 * L.slot_stride, 0);
+  auto emits = [&](const TileInfo &T, int newc, int s) -> bool {
+    const int oldc = L.new2old[newc];
+    const int oth = other_cell(cf[(size_t)oldc * 6 + s]);
+    if (oth < 0 || oth >= n_owned) return true;
+    const int on = L.old2new[oth];
+    if (on < T.cell_start || on >= T.cell_start + T.cell_count) return true;
+    return on < newc;
+  };
+  std::vector<long> fstart(n_tiles + 1, 0);
+  int max_faces = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_faces)
+  for (long k = 0; k < n_tiles; ++k) {
+    const TileInfo &T = L.tiles[k];
+    int cnt = 0;
+    for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c)
+      for (int s = 0; s < 6; ++s) cnt += emits(T, c, s) ? 1 : 0;
+    L.tiles[k].face_count = cnt;
+    max_faces = std::max(max_faces, cnt);
+  }
+  if (max_faces >= 32768) return ma_set_error(MA_ERR_INVALID, "tile has more than 32767 faces; use smaller tile_dims");
+  L.max_tile_faces = max_faces;
+  long real = 0;
+  for (long k = 0; k < n_tiles; ++k) {
+    L.tiles[k].face_start = (int)fstart[k];
+    fstart[k + 1] = fstart[k] + round_up(L.tiles[k].face_count, 16);
+    real += L.tiles[k].face_count;
+    if (fstart[k + 1] >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 tile faces");
+  }
+  L.n_tile_faces = fstart[n_tiles];
+  L.n_tile_faces_real = real;
+  const size_t NF = (size_t)L.n_tile_faces;
+  L.face_geom.assign(12 * NF, 0.0);
+  L.face_left.assign(NF, 0);
+  L.face_right.assign(NF, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (long k = 0; k < n_tiles; ++k) {
+    const TileInfo &T = L.tiles[k];
+    int e = 0;
+    for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c) {
+      const int oldc = L.new2old[c];
+      for (int s = 0; s < 6; ++s) {
+        if (!emits(T, c, s)) continue;
+        const uint32_t ref = cf[(size_t)oldc * 6 + s];
+        const int side = (int)(ref & 1);
+        const FaceSrc src = face_src(ref);
+        const size_t j = (size_t)T.face_start + e;
+        const size_t fi = (size_t)src.index;
+        for (int d = 0; d < 3; ++d) {
+          L.face_geom[(0 + d) * NF + j] = src.f->face_normal[3 * fi + d];
+          L.face_geom[(3 + d) * NF + j] = src.f->face_tangent[3 * fi + d];
+          L.face_geom[(6 + d) * NF + j] = src.f->face_binormal[3 * fi + d];
+          L.face_geom[(9 + d) * NF + j] = src.f->coordinates[3 * fi + d];
+        }
+        L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
+        if (src.bc_type >= 0) {
+          L.face_left[j] = c;
+          L.face_right[j] = bc_code(src.bc_type);
+        } else {
+          const int oth_old = src.f->face_cell_conn[2 * fi + (1 - side)];
+          const int oth_new = L.old2new[oth_old];
+          L.face_left[j] = side == 0 ? c : oth_new;
+          L.face_right[j] = side == 0 ? oth_new : c;
+          if (oth_old < n_owned && oth_new >= T.cell_start && oth_new < T.cell_start + T.cell_count) {
+            const int os = src.f->cell_flux_index[2 * fi + (1 - side)];
+            L.slot_face[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(e | ((1 - side) << 15));
+          }
+        }
+        ++e;
+      }
+    }
+  }
+
+  // ---- 6. halo lists (renumbered), grouped by peer
+  if (n_ghost > 0) {
+    long so = 0, ro = 0;
+    for (int p = 0; p < mesh.num_ranks; ++p) {
+      const int sc = mesh.send_count[p], rc = mesh.recv_count[p];
+      if (sc < 0 || rc < 0) return ma_set_error(MA_ERR_INVALID, "mesh: negative send/recv count");
+      if (p == mesh.my_rank || (sc == 0 && rc == 0)) {
+        so += sc, ro += rc;
+        continue;
+      }
+      L.peer_rank.push_back(p);
+      L.peer_send_count.push_back(sc);
+      L.peer_recv_count.push_back(rc);
+      for (int i = 0; i < sc; ++i) {
+        const int id = mesh.send_local_ids[so + i];
+        if (id < 0 || id >= n_owned) return ma_set_error(MA_ERR_INVALID, "mesh: send_local_ids out of range");
+        L.send_ids.push_back(L.old2new[id]);
+      }
+      for (int i = 0; i < rc; ++i) {
+        const int id = mesh.recv_local_ids[ro + i];
+        if (id < n_owned || id >= n_cells) return ma_set_error(MA_ERR_INVALID, "mesh: recv_local_ids must be ghosts");
+        L.recv_ids.push_back(L.old2new[id]);
+      }
+      so += sc, ro += rc;
+    }
+  }
+  return MA_OK;
+}
+
+}  // namespace ma

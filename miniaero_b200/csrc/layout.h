@@ -1,0 +1,58 @@
+// Host-side construction of the device data layout: cell renumbering into spatial tiles,
+// tile-packed structure-of-arrays face lists, cell -> tile-face slot maps.
+//
+// This replaces the reference's Faces<Device>/Cells<Device> containers (Faces.h:42-71, Cells.h:41-76),
+// its BinSort face permutation (Faces.h:128-144) and its 6-slot scratch arrays cell_flux_ /
+// cell_gradient_ / stored_{min,max,limiter}_ (Cells.h:70-71, StencilLimiter.h:525-527).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "miniaero_b200.h"
+
+namespace ma {
+
+// Boundary faces are encoded in the tile-face "right cell" entry as -1 - ma_bc_type.
+inline int bc_code(int type) { return -1 - type; }
+
+struct TileInfo {
+  int cell_start;  // first (renumbered) cell of the tile
+  int cell_count;
+  int face_start;  // first entry of the tile in the tile-packed face arrays
+  int face_count;
+};
+
+struct HostLayout {
+  int n_owned = 0, n_ghost = 0;
+  int stride = 0;  // SoA component stride of cell arrays (>= n_owned + n_ghost, multiple of 32)
+  int tile_dims[3] = {0, 0, 0};
+  int max_tile_cells = 0, max_tile_faces = 0;
+  int n_tiles = 0;
+  int n_interior_tiles = 0;  // tiles [0, n_interior_tiles) touch no ghost cell
+  long n_tile_faces = 0;     // length of the tile-packed face arrays (with per-tile padding)
+  long n_tile_faces_real = 0;
+
+  std::vector<int> new2old, old2new;  // owned + ghost cells
+  std::vector<TileInfo> tiles;
+
+  // cell SoA (renumbered): xyz[3][stride], vol[stride]
+  std::vector<double> cell_xyz, cell_vol;
+  // slot map: slot_face[s][cell] (owned cells only, stride = n_owned rounded up to 32):
+  // bits 0..14 tile-local face index, bit 15 = 1 when the cell is elem2 (right) of the face
+  std::vector<uint16_t> slot_face;
+  int slot_stride = 0;
+
+  // tile-packed face SoA, length n_tile_faces each: geometry component g of face j at geom[g*n_tile_faces + j]
+  // g: 0-2 normal, 3-5 tangent, 6-8 binormal, 9-11 centroid
+  std::vector<double> face_geom;
+  std::vector<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
+
+  // halo lists in renumbered ids, grouped by neighbour rank ascending
+  std::vector<int> send_ids, recv_ids;
+  std::vector<int> peer_rank, peer_send_count, peer_recv_count;
+};
+
+// Returns MA_OK or sets the error text.  tile_dims: requested cells per tile per direction.
+int build_layout(const ma_mesh &mesh, const int tile_dims[3], HostLayout &L);
+
+}  // namespace ma

@@ -1,0 +1,737 @@
+// C-ABI implementation of the solver object: the drop-in for TimeSolverExplicitRK4<Device>
+// (TimeSolverExplicitRK4.h:160-539).  Owns the device copy of the mesh in the tile-packed SoA layout,
+// the four state vectors, gradient and limiter fields, the halo buffers, streams and events.
+//
+// One RK stage (second order):   grad_limiter_kernel  ->  [halo: gradient+limiter]  ->  flux_rk_kernel
+//                                ->  [halo: next stage state]
+// versus the reference's ~37 parallel_for launches, 5 host-staged exchanges and ~12 fences per stage
+// (TimeSolverExplicitRK4.h:352-486).  With overlap_halo the tiles that touch no ghost cell run while
+// the exchanges are in flight on a second stream.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "comm.h"
+#include "host_common.h"
+#include "kernels.h"
+#include "layout.h"
+#include "miniaero_b200.h"
+
+namespace {
+
+#define MA_CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return ma_set_error(MA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+  } while (0)
+
+// ---- layout-independent helper kernels -----------------------------------------------------------------
+// caller order AoS [n_owned][ncomp]  <->  device SoA [ncomp][stride] in renumbered order
+__global__ void soa_to_caller_kernel(const double *__restrict__ soa, int stride, int ncomp, int n_owned,
+                                     const int *__restrict__ old2new, double *__restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n_owned * ncomp) return;
+  const int cell = (int)(i / ncomp), k = (int)(i % ncomp);
+  out[i] = soa[(size_t)k * stride + old2new[cell]];
+}
+__global__ void caller_to_soa_kernel(const double *__restrict__ in, int stride, int ncomp, int n_owned,
+                                     const int *__restrict__ old2new, double *__restrict__ soa) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)n_owned * ncomp) return;
+  const int cell = (int)(i / ncomp), k = (int)(i % ncomp);
+  soa[(size_t)k * stride + old2new[cell]] = in[i];
+}
+// halo pack / unpack (CopyGhost.h:93-211): buf[i][col0 + k] <-> field[k][ids[i]]
+__global__ void pack_kernel(const double *__restrict__ field, int stride, int ncomp, const int *__restrict__ ids,
+                            int count, double *__restrict__ buf, int row, int col0) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)count * ncomp) return;
+  const int cell = (int)(i / ncomp), k = (int)(i % ncomp);
+  buf[(size_t)cell * row + col0 + k] = field[(size_t)k * stride + ids[cell]];
+}
+__global__ void unpack_kernel(double *__restrict__ field, int stride, int ncomp, const int *__restrict__ ids,
+                              int count, const double *__restrict__ buf, int row, int col0) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)count * ncomp) return;
+  const int cell = (int)(i / ncomp), k = (int)(i % ncomp);
+  field[(size_t)k * stride + ids[cell]] = buf[(size_t)cell * row + col0 + k];
+}
+
+template <class T>
+int dev_alloc(T **p, size_t n, size_t *tally) {
+  *p = nullptr;
+  if (n == 0) return MA_OK;
+  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess)
+    return ma_set_error(e == cudaErrorMemoryAllocation ? MA_ERR_NOMEM : MA_ERR_CUDA,
+                        std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
+  if (tally) *tally += n * sizeof(T);
+  return MA_OK;
+}
+template <class T>
+int dev_upload(T **p, const std::vector<T> &v, size_t *tally) {
+  int rc = dev_alloc(p, v.size(), tally);
+  if (rc) return rc;
+  if (!v.empty()) MA_CUDA_TRY(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MA_OK;
+}
+
+}  // namespace
+
+struct ma_solver {
+  ma_options opt;
+  ma_solver_config cfg;
+  bool strict = false, second = false, viscous = false, need_grad = false;
+  int device = 0;
+  // layout (small host pieces kept)
+  int n_owned = 0, n_ghost = 0, stride = 0, n_tiles = 0, n_interior_tiles = 0;
+  long n_tile_faces_real = 0;
+  std::vector<int> peer_rank, peer_send, peer_recv;
+  int n_send = 0, n_recv = 0;
+  // device
+  ma::DevMesh dm;
+  ma::TileInfoDev *d_tiles = nullptr;
+  double *d_xyz = nullptr, *d_vol = nullptr, *d_geom = nullptr;
+  uint16_t *d_slot = nullptr;
+  int *d_fl = nullptr, *d_fr = nullptr, *d_old2new = nullptr, *d_send_ids = nullptr, *d_recv_ids = nullptr;
+  double *d_Un = nullptr, *d_Acc = nullptr, *d_Wa = nullptr, *d_Wb = nullptr, *d_grad = nullptr, *d_lim = nullptr;
+  double *d_sendbuf = nullptr, *d_recvbuf = nullptr, *d_stage = nullptr;
+  size_t stage_elems = 0;
+  size_t device_bytes = 0;
+  const double *last_stage_state = nullptr;
+  // execution
+  cudaStream_t st = nullptr, cs = nullptr;
+  bool own_stream = false, own_cs = false;
+  cudaEvent_t ev_u = nullptr, ev_a = nullptr, ev_gl = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
+  int flux_threads = 256, grad_threads = 128;
+  bool profiling = false;
+  bool u_pending = false;  // a state exchange is in flight on cs (ev_u marks its end)
+  ma_timing tm;
+  double sim_time = 0.0;
+  long time_it = 0;
+};
+
+namespace {
+
+struct Api {
+  decltype(&ma_fast::launch_grad_limiter) grad;
+  decltype(&ma_fast::launch_flux_rk) flux;
+  decltype(&ma_fast::flux_rk_prepare) prepare;
+  decltype(&ma_fast::launch_initial_conditions) ic;
+};
+Api api_of(bool strict) {
+  if (strict)
+    return {&ma_strict::launch_grad_limiter, &ma_strict::launch_flux_rk, &ma_strict::flux_rk_prepare,
+            &ma_strict::launch_initial_conditions};
+  return {&ma_fast::launch_grad_limiter, &ma_fast::launch_flux_rk, &ma_fast::flux_rk_prepare,
+          &ma_fast::launch_initial_conditions};
+}
+
+int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return ma_set_error(MA_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+  if (device < 0 || device >= count) return ma_set_error(MA_ERR_INVALID, "device ordinal out of range");
+  MA_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp p;
+  MA_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+  if (p.major != 10)
+    return ma_set_error(MA_ERR_CUDA, std::string("device '") + p.name + "' is sm_" + std::to_string(p.major) +
+                                         std::to_string(p.minor) + "; this library carries sm_100a code only");
+  return MA_OK;
+}
+
+// one halo round on stream `s`: pack the listed fields of the send cells, exchange, unpack into the ghosts
+struct FieldRef {
+  double *ptr;
+  int ncomp;
+};
+int halo_exchange(ma_solver *S, const FieldRef *fields, int nfields, cudaStream_t s) {
+  if (S->n_ghost == 0) return MA_OK;
+  int row = 0;
+  for (int f = 0; f < nfields; ++f) row += fields[f].ncomp;
+  const int threads = 256;
+  int col = 0;
+  for (int f = 0; f < nfields; ++f) {
+    const long work = (long)S->n_send * fields[f].ncomp;
+    if (work)
+      pack_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, s>>>(
+          fields[f].ptr, S->stride, fields[f].ncomp, S->d_send_ids, S->n_send, S->d_sendbuf, row, col);
+    col += fields[f].ncomp;
+    S->tm.kernel_launches++;
+  }
+  MA_CUDA_TRY(cudaGetLastError());
+  int rc = ma::comm_exchange(S->cfg.comm, S->d_sendbuf, S->d_recvbuf, row, (int)S->peer_rank.size(),
+                             S->peer_rank.data(), S->peer_send.data(), S->peer_recv.data(), s);
+  if (rc) return rc;
+  col = 0;
+  for (int f = 0; f < nfields; ++f) {
+    const long work = (long)S->n_recv * fields[f].ncomp;
+    if (work)
+      unpack_kernel<<<(unsigned)((work + threads - 1) / threads), threads, 0, s>>>(
+          fields[f].ptr, S->stride, fields[f].ncomp, S->d_recv_ids, S->n_recv, S->d_recvbuf, row, col);
+    col += fields[f].ncomp;
+    S->tm.kernel_launches++;
+  }
+  MA_CUDA_TRY(cudaGetLastError());
+  return MA_OK;
+}
+
+// start the exchange of a freshly written state vector on the comm stream; ev_u marks completion
+int start_state_exchange(ma_solver *S, double *state) {
+  if (S->n_ghost == 0) return MA_OK;
+  MA_CUDA_TRY(cudaEventRecord(S->ev_b, S->st));
+  MA_CUDA_TRY(cudaStreamWaitEvent(S->cs, S->ev_b, 0));
+  FieldRef f = {state, 5};
+  int rc = halo_exchange(S, &f, 1, S->cs);
+  if (rc) return rc;
+  MA_CUDA_TRY(cudaEventRecord(S->ev_u, S->cs));
+  S->u_pending = true;
+  return MA_OK;
+}
+int wait_state_exchange(ma_solver *S) {
+  if (S->u_pending) {
+    MA_CUDA_TRY(cudaStreamWaitEvent(S->st, S->ev_u, 0));
+    S->u_pending = false;
+  }
+  return MA_OK;
+}
+
+struct ProfScope {  // optional per-kernel-class timing (serialises; off by default)
+  ma_solver *S;
+  double *acc;
+  ProfScope(ma_solver *s, double *a) : S(s), acc(a) {
+    if (S->profiling) cudaEventRecord(S->ev_p0, S->st);
+  }
+  ~ProfScope() {
+    if (S->profiling) {
+      cudaEventRecord(S->ev_p1, S->st);
+      cudaEventSynchronize(S->ev_p1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, S->ev_p0, S->ev_p1);
+      *acc += ms * 1e-3;
+    }
+  }
+};
+
+int run_stage(ma_solver *S, const Api &K, int k) {
+  static const double alpha[4] = {0.0, 1.0 / 2.0, 1.0 / 2.0, 1.0};                  // TimeSolverExplicitRK4.h:188-191
+  static const double beta[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};       // :192-195
+  const double *W = (k == 0) ? S->d_Un : ((k & 1) ? S->d_Wa : S->d_Wb);
+  double *Wnext = (k == 0) ? S->d_Wa : (k == 1) ? S->d_Wb : (k == 2) ? S->d_Wa : S->d_Un;
+  ma::StageArgs a;
+  a.W = W;
+  a.Un = S->d_Un;
+  a.AccIn = S->d_Acc;
+  a.AccOut = S->d_Acc;
+  a.Wnext = Wnext;
+  a.grad = S->d_grad;
+  a.lim = S->d_lim;
+  a.dt = S->opt.dt;
+  a.alpha_next = (k < 3) ? alpha[k + 1] : 0.0;
+  a.beta = beta[k];
+  a.kind = (k == 0) ? 0 : (k == 3) ? 2 : 1;
+  S->last_stage_state = W;
+  const int nint = S->n_ghost ? S->n_interior_tiles : S->n_tiles;
+  const int nbnd = S->n_tiles - nint;
+
+  if (S->need_grad) {
+    {
+      ProfScope p(S, &S->tm.grad_seconds);
+      MA_CUDA_TRY(K.grad(S->dm, W, S->d_grad, S->d_lim, S->second, 0, nint, S->grad_threads, S->st));
+      S->tm.kernel_launches += nint > 0;
+      int rc = wait_state_exchange(S);
+      if (rc) return rc;
+      MA_CUDA_TRY(K.grad(S->dm, W, S->d_grad, S->d_lim, S->second, nint, nbnd, S->grad_threads, S->st));
+      S->tm.kernel_launches += nbnd > 0;
+    }
+    if (S->n_ghost) {  // gradient (+ limiter) halo: GreenGauss.h:324-338, StencilLimiter.h:618-631
+      ProfScope p(S, &S->tm.halo_seconds);
+      MA_CUDA_TRY(cudaEventRecord(S->ev_a, S->st));
+      MA_CUDA_TRY(cudaStreamWaitEvent(S->cs, S->ev_a, 0));
+      FieldRef f[2] = {{S->d_grad, 15}, {S->d_lim, 5}};
+      int rc = halo_exchange(S, f, S->second ? 2 : 1, S->cs);
+      if (rc) return rc;
+      MA_CUDA_TRY(cudaEventRecord(S->ev_gl, S->cs));
+    }
+    {
+      ProfScope p(S, &S->tm.flux_seconds);
+      MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, 0, nint, S->flux_threads, S->st));
+      S->tm.kernel_launches += nint > 0;
+      if (S->n_ghost) MA_CUDA_TRY(cudaStreamWaitEvent(S->st, S->ev_gl, 0));
+      MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
+      S->tm.kernel_launches += nbnd > 0;
+    }
+  } else {
+    ProfScope p(S, &S->tm.flux_seconds);
+    MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, 0, nint, S->flux_threads, S->st));
+    S->tm.kernel_launches += nint > 0;
+    int rc = wait_state_exchange(S);
+    if (rc) return rc;
+    MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
+    S->tm.kernel_launches += nbnd > 0;
+  }
+  {
+    ProfScope p(S, &S->tm.halo_seconds);
+    int rc = start_state_exchange(S, Wnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
+    if (rc) return rc;
+    if (S->profiling) {
+      rc = wait_state_exchange(S);
+      if (rc) return rc;
+    }
+  }
+  return MA_OK;
+}
+
+int ensure_staging(ma_solver *S, size_t elems) {
+  if (S->stage_elems >= elems) return MA_OK;
+  if (S->d_stage) {
+    cudaFree(S->d_stage);
+    S->device_bytes -= S->stage_elems * sizeof(double);
+    S->d_stage = nullptr;
+    S->stage_elems = 0;
+  }
+  int rc = dev_alloc(&S->d_stage, elems, &S->device_bytes);
+  if (rc) return rc;
+  S->stage_elems = elems;
+  return MA_OK;
+}
+
+int download_field(ma_solver *S, const double *soa, int ncomp, double *host) {
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  int rc = wait_state_exchange(S);
+  if (rc) return rc;
+  const size_t elems = (size_t)S->n_owned * ncomp;
+  rc = ensure_staging(S, elems);
+  if (rc) return rc;
+  const int threads = 256;
+  soa_to_caller_kernel<<<(unsigned)((elems + threads - 1) / threads), threads, 0, S->st>>>(
+      soa, S->stride, ncomp, S->n_owned, S->d_old2new, S->d_stage);
+  MA_CUDA_TRY(cudaGetLastError());
+  MA_CUDA_TRY(cudaMemcpyAsync(host, S->d_stage, elems * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+  MA_CUDA_TRY(cudaStreamSynchronize(S->st));
+  return MA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ma_solver_config_default(ma_solver_config *cfg) {
+  if (!cfg) return;
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->device = 0;
+  cfg->arith = MA_ARITH_FAST;
+  cfg->tile_dims[0] = cfg->tile_dims[1] = cfg->tile_dims[2] = 0;
+  cfg->block_threads = 0;
+  cfg->comm = nullptr;
+  cfg->overlap_halo = 1;
+  cfg->stream = nullptr;
+}
+
+void ma_solver_destroy(ma_solver *S) {
+  if (!S) return;
+  cudaSetDevice(S->device);
+  if (S->st) cudaStreamSynchronize(S->st);
+  if (S->cs) cudaStreamSynchronize(S->cs);
+  void *ptrs[] = {S->d_tiles, S->d_xyz,  S->d_vol,  S->d_geom, S->d_slot,    S->d_fl,      S->d_fr,   S->d_old2new,
+                  S->d_send_ids, S->d_recv_ids, S->d_Un, S->d_Acc, S->d_Wa, S->d_Wb, S->d_grad, S->d_lim,
+                  S->d_sendbuf, S->d_recvbuf, S->d_stage};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  cudaEvent_t evs[] = {S->ev_u, S->ev_a, S->ev_gl, S->ev_b, S->ev_t0, S->ev_t1, S->ev_p0, S->ev_p1};
+  for (cudaEvent_t e : evs)
+    if (e) cudaEventDestroy(e);
+  if (S->own_cs && S->cs) cudaStreamDestroy(S->cs);
+  if (S->own_stream && S->st) cudaStreamDestroy(S->st);
+  delete S;
+}
+
+int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver_config *cfg_in, ma_solver **out) {
+  if (!mesh || !opt || !out) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: null argument");
+  *out = nullptr;
+  ma_solver_config cfg;
+  if (cfg_in)
+    cfg = *cfg_in;
+  else
+    ma_solver_config_default(&cfg);
+  if (cfg.arith != MA_ARITH_FAST && cfg.arith != MA_ARITH_STRICT)
+    return ma_set_error(MA_ERR_INVALID, "ma_solver_create: arith must be MA_ARITH_FAST or MA_ARITH_STRICT");
+  if (mesh->num_ghosts > 0 && !cfg.comm)
+    return ma_set_error(MA_ERR_INVALID, "ma_solver_create: mesh has ghost cells but no communicator was given");
+  if (!(opt->dt > 0.0)) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: dt must be positive");
+  int rc = check_device(cfg.device);
+  if (rc) return rc;
+
+  // tile size: 8x8x8 unless told otherwise
+  int td[3];
+  for (int d = 0; d < 3; ++d) td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : 8;
+  ma::HostLayout L;
+  rc = ma::build_layout(*mesh, td, L);
+  if (rc) return rc;
+
+  ma_solver *S = new ma_solver();
+  std::memset(&S->tm, 0, sizeof(S->tm));
+  std::memset(&S->dm, 0, sizeof(S->dm));
+  S->opt = *opt;
+  S->cfg = cfg;
+  S->device = cfg.device;
+  S->strict = cfg.arith == MA_ARITH_STRICT;
+  S->second = opt->second_order_space != 0;
+  S->viscous = opt->viscous != 0;
+  S->need_grad = S->second || S->viscous;  // TimeSolverExplicitRK4.h:383
+  S->n_owned = L.n_owned, S->n_ghost = L.n_ghost, S->stride = L.stride;
+  S->n_tiles = L.n_tiles, S->n_interior_tiles = L.n_interior_tiles;
+  S->n_tile_faces_real = L.n_tile_faces_real;
+  S->peer_rank = L.peer_rank, S->peer_send = L.peer_send_count, S->peer_recv = L.peer_recv_count;
+  S->n_send = (int)L.send_ids.size(), S->n_recv = (int)L.recv_ids.size();
+  if (cfg.block_threads > 0) S->flux_threads = std::min(256, (cfg.block_threads + 31) / 32 * 32);
+
+#define MA_TRY(expr)        \
+  do {                      \
+    rc = (expr);            \
+    if (rc) {               \
+      ma_solver_destroy(S); \
+      return rc;            \
+    }                       \
+  } while (0)
+#define MA_CU(expr)                                                                                    \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      ma_solver_destroy(S);                                                                            \
+      return ma_set_error(MA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    }                                                                                                  \
+  } while (0)
+
+  if (cfg.stream) {
+    S->st = (cudaStream_t)cfg.stream;
+  } else {
+    MA_CU(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+    S->own_stream = true;
+  }
+  if (S->n_ghost && cfg.overlap_halo) {
+    MA_CU(cudaStreamCreateWithFlags(&S->cs, cudaStreamNonBlocking));
+    S->own_cs = true;
+  } else {
+    S->cs = S->st;
+  }
+  cudaEvent_t *evs[] = {&S->ev_u, &S->ev_a, &S->ev_gl, &S->ev_b};
+  for (cudaEvent_t *e : evs) MA_CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  MA_CU(cudaEventCreate(&S->ev_t0));
+  MA_CU(cudaEventCreate(&S->ev_t1));
+  MA_CU(cudaEventCreate(&S->ev_p0));
+  MA_CU(cudaEventCreate(&S->ev_p1));
+
+  // ---- upload the layout
+  {
+    std::vector<ma::TileInfoDev> tiles(L.tiles.size());
+    for (size_t i = 0; i < tiles.size(); ++i)
+      tiles[i] = {L.tiles[i].cell_start, L.tiles[i].cell_count, L.tiles[i].face_start, L.tiles[i].face_count};
+    MA_TRY(dev_upload(&S->d_tiles, tiles, &S->device_bytes));
+  }
+  MA_TRY(dev_upload(&S->d_xyz, L.cell_xyz, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_vol, L.cell_vol, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_geom, L.face_geom, &S->device_bytes));
+  std::vector<double>().swap(L.face_geom);
+  MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_fr, L.face_right, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_old2new, L.old2new, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_send_ids, L.send_ids, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_recv_ids, L.recv_ids, &S->device_bytes));
+  const size_t sv = (size_t)5 * S->stride;
+  double **states[] = {&S->d_Un, &S->d_Acc, &S->d_Wa, &S->d_Wb};
+  for (double **p : states) {
+    MA_TRY(dev_alloc(p, sv, &S->device_bytes));
+    MA_CU(cudaMemset(*p, 0, sv * sizeof(double)));  // ghosts start at zero like the reference's Views
+  }
+  if (S->need_grad) {
+    MA_TRY(dev_alloc(&S->d_grad, (size_t)15 * S->stride, &S->device_bytes));
+    MA_CU(cudaMemset(S->d_grad, 0, (size_t)15 * S->stride * sizeof(double)));
+  }
+  if (S->second) {
+    MA_TRY(dev_alloc(&S->d_lim, sv, &S->device_bytes));
+    MA_CU(cudaMemset(S->d_lim, 0, sv * sizeof(double)));
+  }
+  if (S->n_ghost) {
+    MA_TRY(dev_alloc(&S->d_sendbuf, (size_t)20 * S->n_send, &S->device_bytes));
+    MA_TRY(dev_alloc(&S->d_recvbuf, (size_t)20 * S->n_recv, &S->device_bytes));
+  }
+
+  ma::DevMesh &m = S->dm;
+  m.n_owned = S->n_owned;
+  m.n_cells = S->n_owned + S->n_ghost;
+  m.stride = S->stride;
+  m.n_tiles = S->n_tiles;
+  m.slot_stride = L.slot_stride;
+  m.n_tile_faces = L.n_tile_faces;
+  m.flux_smem_stride = (L.max_tile_faces + 15) / 16 * 16 + 1;  // odd stride: conflict-free across components
+  m.tiles = S->d_tiles;
+  m.cell_xyz = S->d_xyz;
+  m.cell_vol = S->d_vol;
+  m.slot_face = S->d_slot;
+  m.face_geom = S->d_geom;
+  m.face_left = S->d_fl;
+  m.face_right = S->d_fr;
+  // inflow state, TimeSolverExplicitRK4.h:218-223
+  m.inflow[0] = 0.5805, m.inflow[1] = 503.96, m.inflow[2] = 0.0, m.inflow[3] = 0.0, m.inflow[4] = 343750.0;
+  const int smem = 5 * m.flux_smem_stride * (int)sizeof(double);
+  if (smem > 227 * 1024) {
+    ma_solver_destroy(S);
+    return ma_set_error(MA_ERR_INVALID, "tile needs more than 227 KB of shared memory; use smaller tile_dims");
+  }
+  MA_CU(api_of(S->strict).prepare(smem));
+  S->tm.device_bytes = S->device_bytes;
+  S->tm.num_tiles = S->n_tiles;
+  S->tm.tile_faces_total = (int)std::min<long>(L.n_tile_faces_real, 2147483647L);
+  MA_CU(cudaDeviceSynchronize());
+#undef MA_TRY
+#undef MA_CU
+  *out = S;
+  return MA_OK;
+}
+
+int ma_solver_initialize(ma_solver *S) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  const Api K = api_of(S->strict);
+  const size_t sv = (size_t)5 * S->stride * sizeof(double);
+  MA_CUDA_TRY(cudaMemsetAsync(S->d_Un, 0, sv, S->st));
+  const double midx = S->opt.lx / 2.0;  // TimeSolverExplicitRK4.h:217
+  MA_CUDA_TRY(K.ic(S->dm, S->d_Un, S->opt.problem_type, midx, S->st));
+  S->sim_time = 0.0;
+  S->time_it = 0;
+  int rc = start_state_exchange(S, S->d_Un);
+  if (rc) return rc;
+  return MA_OK;
+}
+
+int ma_solver_step(ma_solver *S, int nsteps) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  if (nsteps < 0) return ma_set_error(MA_ERR_INVALID, "nsteps must be >= 0");
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  const Api K = api_of(S->strict);
+  MA_CUDA_TRY(cudaEventRecord(S->ev_t0, S->st));
+  for (int it = 0; it < nsteps; ++it) {
+    S->sim_time += S->opt.dt;  // TimeSolverExplicitRK4.h:343
+    S->time_it++;
+    for (int k = 0; k < 4; ++k) {
+      int rc = run_stage(S, K, k);
+      if (rc) return rc;
+    }
+  }
+  int rc = wait_state_exchange(S);  // the timed region ends with the ghosts of the new solution in place
+  if (rc) return rc;
+  MA_CUDA_TRY(cudaEventRecord(S->ev_t1, S->st));
+  MA_CUDA_TRY(cudaEventSynchronize(S->ev_t1));
+  MA_CUDA_TRY(cudaGetLastError());
+  float ms = 0;
+  MA_CUDA_TRY(cudaEventElapsedTime(&ms, S->ev_t0, S->ev_t1));
+  S->tm.step_seconds += ms * 1e-3;
+  S->tm.steps += nsteps;
+  S->tm.cell_updates += (long long)nsteps * S->n_owned;
+  return MA_OK;
+}
+
+int ma_solver_solve(ma_solver *S) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = ma_solver_initialize(S);
+  if (rc) return rc;
+  const int rank = ma::comm_rank(S->cfg.comm);
+  const int freq = S->opt.output_frequency > 0 ? S->opt.output_frequency : S->opt.ntimesteps + 1;
+  int done = 0;
+  while (done < S->opt.ntimesteps) {  // progress lines as TimeSolverExplicitRK4.h:346-349
+    const int chunk = std::min(S->opt.ntimesteps - done, freq - (done % freq));
+    rc = ma_solver_step(S, chunk);
+    if (rc) return rc;
+    done += chunk;
+    if (done % freq == 0 && rank == 0)
+      fprintf(stdout, "\nTime Step #%i:  Time = %16.9e; dt = %16.9e\n", done, S->sim_time, S->opt.dt);
+  }
+  rc = ma_solver_synchronize(S);
+  if (rc) return rc;
+  if (rank == 0) {
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stdout, "\n ... Device Run time: %8.2f seconds ...\n", sec);  // TimeSolverExplicitRK4.h:495
+    fflush(stdout);
+  }
+  return MA_OK;
+}
+
+int ma_solver_synchronize(ma_solver *S) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  MA_CUDA_TRY(cudaStreamSynchronize(S->cs));
+  MA_CUDA_TRY(cudaStreamSynchronize(S->st));
+  return MA_OK;
+}
+
+int ma_solver_get_solution(ma_solver *S, double *host) {
+  if (!S || !host) return ma_set_error(MA_ERR_INVALID, "ma_solver_get_solution: null argument");
+  return download_field(S, S->d_Un, 5, host);
+}
+
+int ma_solver_set_solution(ma_solver *S, const double *host) {
+  if (!S || !host) return ma_set_error(MA_ERR_INVALID, "ma_solver_set_solution: null argument");
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  int rc = wait_state_exchange(S);
+  if (rc) return rc;
+  const size_t elems = (size_t)S->n_owned * 5;
+  rc = ensure_staging(S, elems);
+  if (rc) return rc;
+  MA_CUDA_TRY(cudaMemcpyAsync(S->d_stage, host, elems * sizeof(double), cudaMemcpyHostToDevice, S->st));
+  const int threads = 256;
+  caller_to_soa_kernel<<<(unsigned)((elems + threads - 1) / threads), threads, 0, S->st>>>(
+      S->d_stage, S->stride, 5, S->n_owned, S->d_old2new, S->d_Un);
+  MA_CUDA_TRY(cudaGetLastError());
+  return start_state_exchange(S, S->d_Un);
+}
+
+int ma_solver_get_field(ma_solver *S, int field, double *host) {
+  if (!S || !host) return ma_set_error(MA_ERR_INVALID, "ma_solver_get_field: null argument");
+  switch (field) {
+    case MA_FIELD_GRADIENT:
+      if (!S->d_grad) return ma_set_error(MA_ERR_INVALID, "gradients are not computed for first-order inviscid runs");
+      return download_field(S, S->d_grad, 15, host);
+    case MA_FIELD_LIMITER:
+      if (!S->d_lim) return ma_set_error(MA_ERR_INVALID, "limiters are only computed for second-order runs");
+      return download_field(S, S->d_lim, 5, host);
+    case MA_FIELD_STAGE_STATE:
+      if (!S->last_stage_state) return ma_set_error(MA_ERR_INVALID, "no RK stage has run yet");
+      return download_field(S, S->last_stage_state, 5, host);
+    default:
+      return ma_set_error(MA_ERR_INVALID, "unknown field");
+  }
+}
+
+int ma_solver_get_timing(ma_solver *S, ma_timing *t) {
+  if (!S || !t) return ma_set_error(MA_ERR_INVALID, "ma_solver_get_timing: null argument");
+  S->tm.device_bytes = S->device_bytes;
+  *t = S->tm;
+  return MA_OK;
+}
+
+int ma_solver_reset_timing(ma_solver *S) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  S->tm.step_seconds = S->tm.grad_seconds = S->tm.flux_seconds = S->tm.halo_seconds = 0.0;
+  S->tm.steps = S->tm.cell_updates = S->tm.kernel_launches = 0;
+  return MA_OK;
+}
+
+int ma_solver_set_profiling(ma_solver *S, int enabled) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  S->profiling = enabled != 0;
+  return MA_OK;
+}
+
+// ---- probes ----------------------------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+  double *p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int up(const double *h, size_t n) {
+    MA_CUDA_TRY(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(double)));
+    if (h && n) MA_CUDA_TRY(cudaMemcpy(p, h, n * sizeof(double), cudaMemcpyHostToDevice));
+    return MA_OK;
+  }
+  int down(double *h, size_t n) {
+    MA_CUDA_TRY(cudaDeviceSynchronize());
+    if (n) MA_CUDA_TRY(cudaMemcpy(h, p, n * sizeof(double), cudaMemcpyDeviceToHost));
+    return MA_OK;
+  }
+};
+#define MA_RC(expr)   \
+  do {                \
+    int _rc = (expr); \
+    if (_rc) return _rc; \
+  } while (0)
+}  // namespace
+
+int ma_probe_roe_flux(int n, const double *vl, const double *vr, const double *nn, const double *tt, const double *bb,
+                      double *flux, int arith, int device) {
+  if (n < 0 || !vl || !vr || !nn || !tt || !bb || !flux) return ma_set_error(MA_ERR_INVALID, "probe: bad argument");
+  MA_RC(check_device(device));
+  DevBuf a, b, c, d, e, f;
+  const size_t N = (size_t)n;
+  MA_RC(a.up(vl, 5 * N));
+  MA_RC(b.up(vr, 5 * N));
+  MA_RC(c.up(nn, 3 * N));
+  MA_RC(d.up(tt, 3 * N));
+  MA_RC(e.up(bb, 3 * N));
+  MA_RC(f.up(nullptr, 5 * N));
+  MA_CUDA_TRY(arith == MA_ARITH_STRICT ? ma_strict::probe_roe(n, a.p, b.p, c.p, d.p, e.p, f.p, 0)
+                                       : ma_fast::probe_roe(n, a.p, b.p, c.p, d.p, e.p, f.p, 0));
+  return f.down(flux, 5 * N);
+}
+
+int ma_probe_viscous_flux(int n, const double *grad, const double *prim, const double *normal, double *vflux,
+                          int arith, int device) {
+  if (n < 0 || !grad || !prim || !normal || !vflux) return ma_set_error(MA_ERR_INVALID, "probe: bad argument");
+  MA_RC(check_device(device));
+  DevBuf a, b, c, f;
+  const size_t N = (size_t)n;
+  MA_RC(a.up(grad, 15 * N));
+  MA_RC(b.up(prim, 5 * N));
+  MA_RC(c.up(normal, 3 * N));
+  MA_RC(f.up(nullptr, 5 * N));
+  MA_CUDA_TRY(arith == MA_ARITH_STRICT ? ma_strict::probe_viscous(n, a.p, b.p, c.p, f.p, 0)
+                                       : ma_fast::probe_viscous(n, a.p, b.p, c.p, f.p, 0));
+  return f.down(vflux, 5 * N);
+}
+
+int ma_probe_primitives(int n, const double *cons, double *prim, int arith, int device) {
+  if (n < 0 || !cons || !prim) return ma_set_error(MA_ERR_INVALID, "probe: bad argument");
+  MA_RC(check_device(device));
+  DevBuf a, f;
+  const size_t N = (size_t)n;
+  MA_RC(a.up(cons, 5 * N));
+  MA_RC(f.up(nullptr, 5 * N));
+  MA_CUDA_TRY(arith == MA_ARITH_STRICT ? ma_strict::probe_primitives(n, a.p, f.p, 0)
+                                       : ma_fast::probe_primitives(n, a.p, f.p, 0));
+  return f.down(prim, 5 * N);
+}
+
+int ma_probe_venkat(int n, const double *dumax, const double *dumin, const double *du, const double *deltax3,
+                    double *phi, int arith, int device) {
+  if (n < 0 || !dumax || !dumin || !du || !deltax3 || !phi) return ma_set_error(MA_ERR_INVALID, "probe: bad argument");
+  MA_RC(check_device(device));
+  DevBuf a, b, c, d, f;
+  const size_t N = (size_t)n;
+  MA_RC(a.up(dumax, N));
+  MA_RC(b.up(dumin, N));
+  MA_RC(c.up(du, N));
+  MA_RC(d.up(deltax3, N));
+  MA_RC(f.up(nullptr, N));
+  MA_CUDA_TRY(arith == MA_ARITH_STRICT ? ma_strict::probe_venkat(n, a.p, b.p, c.p, d.p, f.p, 0)
+                                       : ma_fast::probe_venkat(n, a.p, b.p, c.p, d.p, f.p, 0));
+  return f.down(phi, N);
+}
+
+int ma_probe_vanalbada(int n, const double *dumax, const double *dumin, const double *du, double *phi, int arith,
+                       int device) {
+  if (n < 0 || !dumax || !dumin || !du || !phi) return ma_set_error(MA_ERR_INVALID, "probe: bad argument");
+  MA_RC(check_device(device));
+  DevBuf a, b, c, f;
+  const size_t N = (size_t)n;
+  MA_RC(a.up(dumax, N));
+  MA_RC(b.up(dumin, N));
+  MA_RC(c.up(du, N));
+  MA_RC(f.up(nullptr, N));
+  MA_CUDA_TRY(arith == MA_ARITH_STRICT ? ma_strict::probe_vanalbada(n, a.p, b.p, c.p, f.p, 0)
+                                       : ma_fast::probe_vanalbada(n, a.p, b.p, c.p, f.p, 0));
+  return f.down(phi, N);
+}
+
+}  // extern "C"
