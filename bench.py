@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""Benchmark of the explicit-RK4 finite-volume step (BASELINE.json metric: cell-updates/s, FP64, % HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one RK4 time step (4 stages) over the whole mesh.  One process per GPU; for N > 1 launch with
+`python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N`.
+torch / torch.distributed are plumbing only (process group, barrier, pinned host buffers); every number is
+produced by libminiaero_b200.so through its C ABI.  There is no CPU fallback: without a B200 the GPU arm
+fails.  `--impl reference` times the UNMODIFIED reference (oracle/_ref, its sources on an OpenMP loop) on
+the host cores; it and the `cpu_baseline` leg are the only places this file executes anything of oracle/.
+
+Workloads (all inputs are generated in code, data = "synthetic"):
+  sod_o2_visc  3-D Sod tube, second order (Green-Gauss + Venkatakrishnan) + viscous flux, 512x512x256 cells
+               PER GPU (BASELINE configs[3] restricted to N GPUs; at N = 1 it is configs[1]'s mesh with the
+               viscous term on: the "full second-order viscous RK4 step" of the north star).  DEFAULT.
+  sod_o2       BASELINE configs[1]: the same mesh, second order, inviscid.
+  flatplate    BASELINE configs[2]: viscous flat plate 1024x512x128 (NoSlip/Inflow/Tangent/Extrapolate).
+The default run also measures the other two single-GPU workloads for a few steps and reports them under
+"also" (N = 1 only).
+"""
+import argparse
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ALGORITHMIC bytes (DESIGN.md "Roofline accounting"): doubles per cell per RK stage
+DBL_SWEEP1 = 53            # gradient + min/max + limiter sweep (second order / viscous only)
+DBL_SWEEP2_O2 = 91         # flux + gather + RK sweep, second order
+DBL_SWEEP2_O1 = 59         # flux + gather + RK sweep, first order
+BYTES_PER_CELL_UPDATE_O2 = 4 * 8 * (DBL_SWEEP1 + DBL_SWEEP2_O2) + 40   # 4648
+BYTES_PER_CELL_UPDATE_O1 = 4 * 8 * DBL_SWEEP2_O1 + 40                  # 1928
+
+WEAK_DIMS = {1: (512, 512, 256), 2: (1024, 512, 256), 4: (1024, 1024, 256), 8: (1024, 1024, 512)}
+
+
+def workload_options(name, n_gpus, cells=None):
+    """-> dict of miniaero.inp values (Options.h:91-99) for `name` on n_gpus GPUs (weak scaling)."""
+    if name in ("sod_o2_visc", "sod_o2"):
+        g = cells or WEAK_DIMS[n_gpus]
+        # the cell size of the 512x512x256 single-GPU mesh is kept as the mesh grows
+        return dict(problem_type=0, lx=0.3048 * g[0] / 512.0, ly=1.0 * g[1] / 512.0, lz=1.0 * g[2] / 256.0, angle=0.0,
+                    nx=g[0], ny=g[1], nz=g[2], dt=5e-7, second_order_space=1, viscous=1 if name == "sod_o2_visc" else 0)
+    if name == "flatplate":
+        base = (1024, 512, 128)
+        g = cells or tuple(b * s for b, s in zip(base, {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n_gpus]))
+        return dict(problem_type=1, lx=2.0 * g[0] / 1024.0, ly=0.032 * g[1] / 512.0, lz=1.0 * g[2] / 128.0, angle=0.0,
+                    nx=g[0], ny=g[1], nz=g[2], dt=3e-8, second_order_space=1, viscous=1)
+    raise SystemExit("unknown workload %r" % name)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+class ClockSampler:
+    """nvidia-smi sampled every 100 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        pw = [float(r[2]) for r in rows if re.match(r"^[0-9.]+$", r[2])]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference on the host cores (oracle/_ref; TEST INFRASTRUCTURE used here only as the timed baseline)
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_sample_dims(opt, steps_total, budget_s, cores):
+    """A bounded sample of the workload: the same physics on the largest mesh of a fixed ladder that the
+    reference (~4e4 cell-updates/s/core second order, ~11 us/cell of mesh setup) finishes within budget_s."""
+    ladder = [(32, 32, 16), (64, 32, 32), (64, 64, 32), (128, 64, 64), (128, 128, 64), (128, 128, 128), (256, 128, 128)]
+    rate = 4.0e4 * cores * (1.0 if opt["second_order_space"] else 3.0)
+    best = ladder[0]
+    for d in ladder:
+        c = d[0] * d[1] * d[2]
+        if c * steps_total / rate + 12e-6 * c <= budget_s:
+            best = d
+    return best
+
+
+def run_reference(workload, steps, warmup, budget_s):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refrun
+    cores = host_cores()
+    base = workload_options(workload, 1)
+    d = reference_sample_dims(base, steps + warmup, budget_s, cores)
+    full = (base["nx"], base["ny"], base["nz"])
+    inp = dict(problem_type=base["problem_type"], lx=base["lx"] * d[0] / full[0], ly=base["ly"] * d[1] / full[1],
+               lz=base["lz"] * d[2] / full[2], angle=base["angle"], nx=d[0], ny=d[1], nz=d[2], ntimesteps=steps + warmup,
+               dt=base["dt"], output_results=0, output_frequency=10 ** 9, second_order=base["second_order_space"],
+               viscous=base["viscous"])
+    exe = refrun.ref_binary("cell", omp=True)
+    if exe is None:
+        return None
+    tmp = tempfile.mkdtemp(prefix="miniaero_bench_ref_")
+    log = os.path.join(tmp, "launch.log")
+    os.environ["MINIAERO_LAUNCH_LOG"] = log
+    try:
+        refrun.run_reference(inp, kind="cell", omp=True, threads=cores, dump=False, workdir=tmp)
+    finally:
+        os.environ.pop("MINIAERO_LAUNCH_LOG", None)
+    ends, functors = [], {}
+    with open(log) as f:
+        for line in f:
+            p = line.split()
+            if p[0] == "step_end":
+                ends.append(float(p[1]))
+            elif p[0] == "functor":
+                functors[p[1]] = (int(p[2]), float(p[3]))
+    # ends[0] = the copy before the time loop, ends[i] = end of time step i (TimeSolverExplicitRK4.h:335,488)
+    assert len(ends) == steps + warmup + 1, (len(ends), steps, warmup)
+    seconds = ends[steps + warmup] - ends[warmup]
+    cells = d[0] * d[1] * d[2]
+    top = sorted(functors.items(), key=lambda kv: -kv[1][1])[:4]
+    total = sum(v[1] for v in functors.values()) or 1.0
+    return {"value": cells * steps / seconds, "seconds": seconds, "cells": cells, "dims": list(d), "cores": cores,
+            "exe": os.path.relpath(exe, ROOT),
+            "top_functors": {re.sub(r"^\d+|IN6Kokkos.*$", "", k): round(v[1] / total, 3) for k, v in top}}
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = run_reference(args.workload, args.steps, args.warmup, budget_s=args.ref_budget)
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/miniAero.cell.omp is not built "
+                          "(oracle/build_ref.sh needs /root/reference; the prebuilt binary normally travels)"}))
+        return 0
+    opt = workload_options(args.workload, max(1, args.gpus))
+    sample = ("%s physics on a %dx%dx%d mesh (%d cells), %d warm-up + %d timed RK4 steps, per-step times read from "
+              "the Kokkos stand-in's launch log" % (args.workload, r["dims"][0], r["dims"][1], r["dims"][2], r["cells"],
+                                                    args.warmup, args.steps))
+    line = {"impl": "reference", "metric": "cell-updates/sec (RK4 steps x cells) FP64", "value": r["value"],
+            "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "cells_per_gpu": opt["nx"] * opt["ny"] * opt["nz"] // max(1, args.gpus),
+                       "second_order": opt["second_order_space"], "viscous": opt["viscous"],
+                       "note": "reference = unmodified miniAero sources (-DCELL_FLUX, -O3 -fopenmp) on a Kokkos "
+                               "stand-in whose parallel_for is an OpenMP static loop; CPU only"},
+            "cpu_baseline": {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
+                             "sample": sample, "cpu": cpu_model(), "top_functors": r["top_functors"]},
+            "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+def build_solver(ma, optd, rank, world, comm, local_rank, keep_mesh=False):
+    opt = ma.Options(ntimesteps=1, output_results=0, output_frequency=10 ** 9, **optd)
+    t0 = time.perf_counter()
+    mesh = ma.Parallel3DMesh.from_options(opt, rank, world).fillMeshData()
+    t1 = time.perf_counter()
+    solver = ma.TimeSolverExplicitRK4(mesh, opt, device=local_rank, comm=comm)
+    t2 = time.perf_counter()
+    info = {"mesh_seconds": t1 - t0, "layout_upload_seconds": t2 - t1, "owned_cells": mesh.num_owned_cells,
+            "ghost_cells": mesh.num_ghosts, "nlocal": list(mesh.nlocal), "nproc": list(mesh.nproc)}
+    if not keep_mesh:
+        solver.release_mesh()
+        del mesh
+    return solver, opt, info
+
+
+def time_steps(solver, steps, warmup, barrier):
+    solver.initialize()
+    solver.step(warmup)
+    solver.synchronize()
+    solver.reset_timing()
+    solver.set_profiling(True)
+    barrier()
+    w0 = time.perf_counter()
+    solver.step(steps)          # CUDA events on the solver's stream bracket exactly these K steps
+    solver.synchronize()
+    w1 = time.perf_counter()
+    solver.set_profiling(False)
+    t = solver.timing()
+    t["wall_seconds"] = w1 - w0
+    t["w0"], t["w1"] = w0, w1
+    return t
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import miniaero_b200 as ma
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch N > 1 with torch.distributed.run)" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        comm = ma.HaloComm.from_torch_distributed(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    cells = tuple(args.cells) if args.cells else None
+    optd = workload_options(args.workload, world, cells)
+    # host memory gate: the host-side mesh + layout of a 64 M-cell block peaks near 0.9 KB/cell; ranks build in
+    # groups that fit the free host memory
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    per_rank = 900.0 * optd["nx"] * optd["ny"] * optd["nz"] / world
+    group = int(max(1, min(world, avail * 0.8 // max(per_rank, 1.0))))
+    solver = None
+    for g0 in range(0, world, group):
+        if g0 <= rank < g0 + group:
+            solver, opt, info = build_solver(ma, optd, rank, world, comm, local_rank)
+        barrier()
+    n_owned = info["owned_cells"]
+    second = bool(optd["second_order_space"])
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t = time_steps(solver, args.steps, args.warmup, barrier)
+    clocks = sampler.stop(t["w0"], t["w1"]) if sampler else None
+    step_s = max_over_ranks(t["step_seconds"])
+    total_cells = sum_over_ranks(float(n_owned))
+    value = total_cells * args.steps / step_s
+
+    # ---- roofline of the dominant kernel (flux + gather + RK), CUDA events recorded over the timed region
+    peak, peak_src = measured_peak()
+    n_flux = 4 * args.steps
+    flux_ms = 1e3 * t["flux_seconds"] / n_flux
+    grad_ms = 1e3 * t["grad_seconds"] / n_flux
+    dbl2 = DBL_SWEEP2_O2 if second else DBL_SWEEP2_O1
+    flux_bytes = 8.0 * dbl2 * n_owned
+    achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        key = "flux_rk_o2" if second else "flux_rk_o1"
+        if key in tj:
+            traffic = tj[key]["dram_bytes_per_cell"] * n_owned
+    bpcu = BYTES_PER_CELL_UPDATE_O2 if (second or optd["viscous"]) else BYTES_PER_CELL_UPDATE_O1
+    roofline = {"bound": "hbm", "kernel": "flux_rk_kernel (flux + gather + RK stage update)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": flux_bytes, "launch_ms": flux_ms,
+                "share_of_step": t["flux_seconds"] / t["step_seconds"],
+                "grad_limiter_kernel": {"launch_ms": grad_ms, "algorithmic_bytes_per_launch": 8.0 * DBL_SWEEP1 * n_owned,
+                                        "achieved": (8.0 * DBL_SWEEP1 * n_owned / (grad_ms * 1e-3) / 1e9) if grad_ms > 0 else None,
+                                        "frac": (8.0 * DBL_SWEEP1 * n_owned / (grad_ms * 1e-3) / 1e9 / peak) if grad_ms > 0 else None},
+                "whole_step": {"bytes_per_cell_update": bpcu, "achieved": bpcu * (value / world) / 1e9,
+                               "frac": bpcu * (value / world) / 1e9 / peak, "frac_of_8TBs_nominal": bpcu * (value / world) / 8e12}}
+    launches = int(t["kernel_launches"])
+
+    # ---- end to end through the C ABI with HOST buffers: every step uploads the state from pinned host memory,
+    # advances one RK4 step and reads the new state back (ma_solver_set_solution / _step / _get_solution)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    nbytes = n_owned * 5 * 8
+    hin = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
+    hout = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
+    solver.solution_into(hin.data_ptr())
+    for _ in range(2):   # warm-up (allocates the device staging buffer)
+        solver.set_solution(hin.data_ptr()); solver.step(1); solver.solution_into(hout.data_ptr())
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.set_solution(hin.data_ptr())
+        solver.step(1)
+        solver.solution_into(hout.data_ptr())   # synchronises the solver's stream
+        hin, hout = hout, hin
+    solver.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - w0)
+    e2e = {"value": total_cells * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+           "d2h_bytes_per_step": nbytes, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "what": "per step: ma_solver_set_solution(pinned host) + ma_solver_step(1) + ma_solver_get_solution(pinned host)"}
+    # the reference's own call shape (Main.C:139-141): one Solve() of K steps, state up once, result down once
+    barrier()
+    w0 = time.perf_counter()
+    solver.set_solution(hin.data_ptr()); solver.step(args.steps); solver.solution_into(hout.data_ptr())
+    solver.synchronize()
+    solve_s = max_over_ranks(time.perf_counter() - w0)
+    e2e["solve_call"] = {"value": total_cells * args.steps / solve_s, "steps": args.steps,
+                         "what": "one upload + K steps + one download (the reference's Solve() shape)"}
+    finite = bool(torch.isfinite(hout).all().item())
+    del hin, hout
+
+    # ---- the other single-GPU workloads, a few steps each (N = 1, default workload only)
+    also = {}
+    if world == 1 and args.also and not args.cells:
+        del solver
+        torch.cuda.empty_cache()
+        for name in ("sod_o2", "flatplate"):
+            if name == args.workload:
+                continue
+            s2, _, i2 = build_solver(ma, workload_options(name, 1), 0, 1, None, local_rank)
+            t2 = time_steps(s2, max(3, args.steps // 4), 3, barrier)
+            v2 = i2["owned_cells"] * t2["steps"] / t2["step_seconds"]
+            also[name] = {"value": v2, "unit": "cell-updates/s", "steps": int(t2["steps"]), "cells": i2["owned_cells"],
+                          "ms_per_step": 1e3 * t2["step_seconds"] / t2["steps"],
+                          "whole_step_roofline_frac": BYTES_PER_CELL_UPDATE_O2 * v2 / 1e9 / peak}
+            del s2
+
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_baseline:
+        r = run_reference(args.workload, 3, 1, budget_s=args.cpu_budget)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
+                   "cpu": cpu_model(), "top_functors": r["top_functors"],
+                   "sample": "%s physics on a %dx%dx%d mesh (%d cells), 1 warm-up + 3 timed RK4 steps of the unmodified "
+                             "reference (-DCELL_FLUX, OpenMP static loop over %d threads)" % (
+                                 args.workload, r["dims"][0], r["dims"][1], r["dims"][2], r["cells"], r["cores"])}
+
+    if rank == 0:
+        line = {"metric": "cell-updates/sec (RK4 steps x cells) FP64", "value": value, "unit": "cell-updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_s / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "mesh": [optd["nx"], optd["ny"], optd["nz"]],
+                           "cells_per_gpu": n_owned, "ghost_cells_rank0": info["ghost_cells"], "blocks": info["nproc"],
+                           "second_order": optd["second_order_space"], "viscous": optd["viscous"], "dt": optd["dt"],
+                           "arith": "fast (FMA contraction, reciprocal multiplication); parity vs the reference in tests/",
+                           "l2": "no flush needed: %.1f GB of solver state per GPU >> 126 MB L2" % (t["device_bytes"] / 1e9),
+                           "device_bytes": int(t["device_bytes"]), "tiles": int(t["num_tiles"]),
+                           "setup_seconds": {k: round(v, 2) for k, v in info.items() if k.endswith("_seconds")}},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "wall_ms_per_step": 1e3 * t["wall_seconds"] / args.steps, "result_finite": finite}
+        if also:
+            line["also"] = also
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sod_o2_visc", choices=["sod_o2_visc", "sod_o2", "flatplate"])
+    ap.add_argument("--cells", type=int, nargs=3, default=None, help="override the GLOBAL mesh (debugging only)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-also", dest="also", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--ref-budget", type=float, default=90.0, help="seconds of CPU work for --impl reference")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    return reference_arm(args) if args.impl == "reference" else gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

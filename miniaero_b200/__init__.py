@@ -195,6 +195,12 @@ class TimeSolverExplicitRK4:
         if h:
             self._lib.ma_solver_destroy(h)
 
+    def release_mesh(self):
+        """Drop the host mesh (the constructor already copied what the device needs); afterwards Solve()
+        cannot write `results.<rank>` (it needs the cell coordinates)."""
+        self._mesh = None
+        self._mesh_keepalive = None
+
     # -- the reference's one public method
     def Solve(self):
         """TimeSolverExplicitRK4::Solve (TimeSolverExplicitRK4.h:207-539): initial conditions, ntimesteps RK4

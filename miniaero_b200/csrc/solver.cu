@@ -108,7 +108,13 @@ struct ma_solver {
   cudaStream_t st = nullptr, cs = nullptr;
   bool own_stream = false, own_cs = false;
   cudaEvent_t ev_u = nullptr, ev_a = nullptr, ev_gl = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-  cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;
+  // per-kernel-class timing: event pairs recorded around launches, read back after the step's final sync
+  struct ProfPair {
+    cudaEvent_t a, b;
+    double *acc;
+  };
+  std::vector<ProfPair> prof_pool;
+  size_t prof_used = 0;
   int flux_threads = 256, grad_threads = 128;
   bool profiling = false;
   bool u_pending = false;  // a state exchange is in flight on cs (ev_u marks its end)
@@ -149,6 +155,36 @@ int check_device(int device) {
   return MA_OK;
 }
 
+// Optional per-kernel-class timing (off by default).  An event pair is recorded on the compute stream
+// around the launches of one class; nothing is synchronised here, so the timed region is not perturbed.
+// collect_profile() reads the pairs back once the step's closing event has completed.
+struct ProfScope {
+  ma_solver *S;
+  ma_solver::ProfPair *p = nullptr;
+  cudaStream_t stream;
+  ProfScope(ma_solver *s, double *acc, cudaStream_t on = nullptr) : S(s), stream(on ? on : s->st) {
+    if (!S->profiling) return;
+    if (S->prof_used == S->prof_pool.size()) {
+      ma_solver::ProfPair np = {nullptr, nullptr, nullptr};
+      if (cudaEventCreate(&np.a) != cudaSuccess || cudaEventCreate(&np.b) != cudaSuccess) return;
+      S->prof_pool.push_back(np);
+    }
+    p = &S->prof_pool[S->prof_used++];
+    p->acc = acc;
+    cudaEventRecord(p->a, stream);
+  }
+  ~ProfScope() {
+    if (p) cudaEventRecord(p->b, stream);
+  }
+};
+void collect_profile(ma_solver *S) {
+  for (size_t i = 0; i < S->prof_used; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, S->prof_pool[i].a, S->prof_pool[i].b) == cudaSuccess) *S->prof_pool[i].acc += ms * 1e-3;
+  }
+  S->prof_used = 0;
+}
+
 // one halo round on stream `s`: pack the listed fields of the send cells, exchange, unpack into the ghosts
 struct FieldRef {
   double *ptr;
@@ -156,6 +192,7 @@ struct FieldRef {
 };
 int halo_exchange(ma_solver *S, const FieldRef *fields, int nfields, cudaStream_t s) {
   if (S->n_ghost == 0) return MA_OK;
+  ProfScope prof(S, &S->tm.halo_seconds, s);  // pack + exchange + unpack, timed on the stream they run on
   int row = 0;
   for (int f = 0; f < nfields; ++f) row += fields[f].ncomp;
   const int threads = 256;
@@ -205,23 +242,6 @@ int wait_state_exchange(ma_solver *S) {
   return MA_OK;
 }
 
-struct ProfScope {  // optional per-kernel-class timing (serialises; off by default)
-  ma_solver *S;
-  double *acc;
-  ProfScope(ma_solver *s, double *a) : S(s), acc(a) {
-    if (S->profiling) cudaEventRecord(S->ev_p0, S->st);
-  }
-  ~ProfScope() {
-    if (S->profiling) {
-      cudaEventRecord(S->ev_p1, S->st);
-      cudaEventSynchronize(S->ev_p1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, S->ev_p0, S->ev_p1);
-      *acc += ms * 1e-3;
-    }
-  }
-};
-
 int run_stage(ma_solver *S, const Api &K, int k) {
   static const double alpha[4] = {0.0, 1.0 / 2.0, 1.0 / 2.0, 1.0};                  // TimeSolverExplicitRK4.h:188-191
   static const double beta[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};       // :192-195
@@ -254,7 +274,6 @@ int run_stage(ma_solver *S, const Api &K, int k) {
       S->tm.kernel_launches += nbnd > 0;
     }
     if (S->n_ghost) {  // gradient (+ limiter) halo: GreenGauss.h:324-338, StencilLimiter.h:618-631
-      ProfScope p(S, &S->tm.halo_seconds);
       MA_CUDA_TRY(cudaEventRecord(S->ev_a, S->st));
       MA_CUDA_TRY(cudaStreamWaitEvent(S->cs, S->ev_a, 0));
       FieldRef f[2] = {{S->d_grad, 15}, {S->d_lim, 5}};
@@ -279,16 +298,7 @@ int run_stage(ma_solver *S, const Api &K, int k) {
     MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
     S->tm.kernel_launches += nbnd > 0;
   }
-  {
-    ProfScope p(S, &S->tm.halo_seconds);
-    int rc = start_state_exchange(S, Wnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
-    if (rc) return rc;
-    if (S->profiling) {
-      rc = wait_state_exchange(S);
-      if (rc) return rc;
-    }
-  }
-  return MA_OK;
+  return start_state_exchange(S, Wnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
 }
 
 int ensure_staging(ma_solver *S, size_t elems) {
@@ -347,9 +357,13 @@ void ma_solver_destroy(ma_solver *S) {
                   S->d_sendbuf, S->d_recvbuf, S->d_stage};
   for (void *p : ptrs)
     if (p) cudaFree(p);
-  cudaEvent_t evs[] = {S->ev_u, S->ev_a, S->ev_gl, S->ev_b, S->ev_t0, S->ev_t1, S->ev_p0, S->ev_p1};
+  cudaEvent_t evs[] = {S->ev_u, S->ev_a, S->ev_gl, S->ev_b, S->ev_t0, S->ev_t1};
   for (cudaEvent_t e : evs)
     if (e) cudaEventDestroy(e);
+  for (auto &pp : S->prof_pool) {
+    if (pp.a) cudaEventDestroy(pp.a);
+    if (pp.b) cudaEventDestroy(pp.b);
+  }
   if (S->own_cs && S->cs) cudaStreamDestroy(S->cs);
   if (S->own_stream && S->st) cudaStreamDestroy(S->st);
   delete S;
@@ -428,8 +442,6 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   for (cudaEvent_t *e : evs) MA_CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   MA_CU(cudaEventCreate(&S->ev_t0));
   MA_CU(cudaEventCreate(&S->ev_t1));
-  MA_CU(cudaEventCreate(&S->ev_p0));
-  MA_CU(cudaEventCreate(&S->ev_p1));
 
   // ---- upload the layout
   {
@@ -537,6 +549,7 @@ int ma_solver_step(ma_solver *S, int nsteps) {
   float ms = 0;
   MA_CUDA_TRY(cudaEventElapsedTime(&ms, S->ev_t0, S->ev_t1));
   S->tm.step_seconds += ms * 1e-3;
+  collect_profile(S);
   S->tm.steps += nsteps;
   S->tm.cell_updates += (long long)nsteps * S->n_owned;
   return MA_OK;

@@ -29,7 +29,9 @@
 #include <memory>
 #include <numeric>
 #include <string>
+#include <map>
 #include <type_traits>
+#include <typeinfo>
 #include <vector>
 
 #define KOKKOS_INLINE_FUNCTION inline
@@ -224,13 +226,63 @@ View<typename View<D, P...>::non_const_value_type *, LayoutStride, HostSpaceDevi
   return s;
 }
 
+namespace standin {
+// Optional launch log (bench.py's CPU baseline): with $MINIAERO_LAUNCH_LOG set, every parallel_for is
+// timed; at exit the file receives one "functor <mangled type> <launches> <seconds>" line per functor
+// type and one "step_end <seconds since first launch>" line per launch of TimeSolverExplicitRK4.h's
+// `copy` functor (:134-153; launched once before the time loop, :335-336, then at the end of every
+// time step, :488-489), which is how per-step times are read without editing the reference.
+struct LaunchLog {
+  bool on = false;
+  std::string path;
+  std::chrono::steady_clock::time_point t0;
+  bool have_t0 = false;
+  std::map<std::string, std::pair<long, double> > per_functor;
+  std::vector<double> step_end;
+  LaunchLog() {
+    const char *p = std::getenv("MINIAERO_LAUNCH_LOG");
+    if (p && *p) {
+      on = true;
+      path = p;
+    }
+  }
+  ~LaunchLog() {
+    if (!on) return;
+    FILE *f = std::fopen(path.c_str(), "w");
+    if (!f) return;
+    for (auto &kv : per_functor)
+      std::fprintf(f, "functor %s %ld %.9f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    for (double t : step_end) std::fprintf(f, "step_end %.9f\n", t);
+    std::fclose(f);
+  }
+  void record(const char *name, std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    if (!have_t0) {
+      t0 = a;
+      have_t0 = true;
+    }
+    auto &e = per_functor[name];
+    e.first += 1;
+    e.second += std::chrono::duration<double>(b - a).count();
+    if (std::strstr(name, "4copyI")) step_end.push_back(std::chrono::duration<double>(b - t0).count());
+  }
+};
+inline LaunchLog &launch_log() {
+  static LaunchLog l;
+  return l;
+}
+}  // namespace standin
+
 template <class Functor>
 void parallel_for(size_t n, const Functor &f) {
   const long nn = (long)n;
+  standin::LaunchLog &log = standin::launch_log();
+  std::chrono::steady_clock::time_point a;
+  if (log.on) a = std::chrono::steady_clock::now();
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
   for (long i = 0; i < nn; ++i) f((int)i);
+  if (log.on) log.record(typeid(Functor).name(), a, std::chrono::steady_clock::now());
 }
 
 namespace Experimental {

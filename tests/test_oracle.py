@@ -1,0 +1,74 @@
+"""CPU tests that PIN the oracle: the unmodified reference built in oracle/_ref (oracle/build_ref.sh) must
+(a) pass the reference's own integration tests — its 6-digit gold files, re-encoded in tests/golden/*.npz —
+at the tolerances of tests/<case>/<case>_test.sh, and (b) reproduce, bit for bit, the full-precision golden
+vectors the GPU parity tests compare against (so those vectors provably come from this oracle)."""
+import numpy as np
+import pytest
+
+import cases
+import parity
+import refrun
+
+pytestmark = pytest.mark.skipif(refrun.ref_binary("cell") is None,
+                                reason="oracle/_ref not built (needs /root/reference once; the binaries travel)")
+
+
+@pytest.mark.parametrize("name", sorted(cases.REFERENCE_TESTS))
+def test_oracle_passes_the_reference_gold_files(name):
+    inp, rel_tol, floor = cases.REFERENCE_TESTS[name]
+    out = refrun.run_reference(inp, kind="cell")
+    g = parity.golden(name)
+    assert out["results"].shape == g["results_gold"].shape
+    assert refrun.numeric_text_diff(out["results"], g["results_gold"], rel_tol, floor) == 0
+    full = refrun.solution_from_dumps(out["dumps"])
+    assert parity.max_ulp(full, g["cell_step%d" % inp["ntimesteps"]]) == 0
+
+
+@pytest.mark.parametrize("name", sorted(cases.EXTRA))
+def test_golden_vectors_come_from_this_oracle(name):
+    inp = cases.EXTRA[name]
+    g = parity.golden(name)
+    for n in (1, 2):
+        out = refrun.run_reference(dict(inp, ntimesteps=n), kind="cell")
+        assert parity.max_ulp(refrun.solution_from_dumps(out["dumps"]), g["cell_step%d" % n]) == 0
+
+
+def test_openmp_build_is_bit_identical_to_serial():
+    """-DCELL_FLUX is deterministic and thread-count independent: the CPU-baseline binary (OpenMP static loop)
+    gives the serial oracle's bits."""
+    inp = dict(cases.EXTRA["sod_o2_visc"], ntimesteps=2)
+    a = refrun.solution_from_dumps(refrun.run_reference(inp, kind="cell")["dumps"])
+    b = refrun.solution_from_dumps(refrun.run_reference(inp, kind="cell", omp=True, threads=4)["dumps"])
+    assert parity.max_ulp(a, b) == 0
+    assert parity.max_ulp(a, parity.golden("sod_o2_visc")["cell_step2"]) == 0
+
+
+def test_reference_noise_floor_between_its_two_builds():
+    """The Makefile-default -DATOMICS_FLUX build differs from -DCELL_FLUX only by summation order: the
+    distance after 100 steps is the reference's own noise floor and sits inside the north-star tolerance."""
+    for name in ("3D_Sod_Serial", "sod_o2_visc", "flatplate_o1"):
+        g = parity.golden(name)
+        linf, l2 = parity.field_errors(g["atomics_step100"], g["cell_step100"])
+        assert linf < parity.TOL_100_STEPS and l2 < parity.TOL_100_STEPS, (name, linf, l2)
+
+
+def test_launch_log_gives_per_step_times(tmp_path, monkeypatch):
+    """bench.py's CPU baseline reads per-time-step timestamps from the stand-in's launch log."""
+    log = tmp_path / "launch.log"
+    monkeypatch.setenv("MINIAERO_LAUNCH_LOG", str(log))
+    refrun.run_reference(dict(cases.EXTRA["sod_o2"], ntimesteps=3, output_results=0), kind="cell", omp=True, threads=2,
+                         dump=False)
+    lines = log.read_text().split("\n")
+    ends = [float(l.split()[1]) for l in lines if l.startswith("step_end")]
+    assert len(ends) == 4 and ends == sorted(ends)
+    assert any(l.startswith("functor") and "compute_face_flux" in l for l in lines)
+
+
+def test_numeric_text_diff_semantics():
+    a = np.array([[1.0, 1e-9], [2.0, 5.0]])
+    assert refrun.numeric_text_diff(a, a) == 0
+    b = a.copy(); b[0, 1] = 5e-9          # below the floor: ignored
+    assert refrun.numeric_text_diff(a, b) == 0
+    b[1, 1] = 5.02                        # 0.4 % > 1e-3
+    assert refrun.numeric_text_diff(a, b) == 1
+    assert refrun.numeric_text_diff(a, b, rel_tol=1e-2) == 0

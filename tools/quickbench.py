@@ -1,5 +1,5 @@
 import sys, time, json
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import miniaero_b200 as ma
 def run(nx,ny,nz,second,visc,ptype=0,steps=5,tile=(0,0,0),bt=0,lx=0.3048,ly=1.0,lz=1.0,dt=5e-7):
     opt=ma.Options(problem_type=ptype,lx=lx,ly=ly,lz=lz,angle=0.0,nx=nx,ny=ny,nz=nz,ntimesteps=steps,dt=dt,second_order_space=second,viscous=visc)
