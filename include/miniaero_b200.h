@@ -126,7 +126,9 @@ void ma_comm_destroy(ma_comm *c);
 
 /* ---- Solver — replaces TimeSolverExplicitRK4<Device> ------------------------------------------ */
 typedef enum ma_arith {
-  MA_ARITH_FAST = 0,  /* FMA contraction + reciprocal multiplication; the production path */
+  MA_ARITH_FAST = 0,  /* FMA contraction, Newton reciprocals / square roots, algebraically regrouped Roe dissipation
+                         and limiter; the production path.  Assumes each face's (normal, tangent, binormal) is an
+                         orthogonal frame with unit tangent (as Face.C:81-96 builds it): checked at create time */
   MA_ARITH_STRICT = 1 /* IEEE-754 evaluation in the reference's source order (no FMA): bit-for-bit
                          comparable with the reference's -DCELL_FLUX build */
 } ma_arith;
@@ -168,8 +170,9 @@ int ma_solver_set_solution(ma_solver *s, const double *host);
 /* Intermediate fields of the most recent RK stage, caller's cell order (parity checks):
  *   MA_FIELD_GRADIENT [num_owned_cells][5][3]  GreenGauss.h:228-270
  *   MA_FIELD_LIMITER  [num_owned_cells][5]     StencilLimiter.h:319-350
- *   MA_FIELD_STAGE_STATE [num_owned_cells][5]  "solution_temp", TimeSolverExplicitRK4.h:355 */
-typedef enum ma_field { MA_FIELD_GRADIENT = 0, MA_FIELD_LIMITER = 1, MA_FIELD_STAGE_STATE = 2 } ma_field;
+ *   MA_FIELD_STAGE_PRIMITIVES [num_owned_cells][5]  (rho,u,v,w,T) = ComputePrimitives (GasModel.h:70-90) of
+ *                        "solution_temp" (TimeSolverExplicitRK4.h:355) — the form the stage state is kept in */
+typedef enum ma_field { MA_FIELD_GRADIENT = 0, MA_FIELD_LIMITER = 1, MA_FIELD_STAGE_PRIMITIVES = 2 } ma_field;
 int ma_solver_get_field(ma_solver *s, int field, double *host);
 
 typedef struct ma_timing {

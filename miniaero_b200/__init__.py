@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (ARITH_FAST, ARITH_STRICT, BC_EXTRAPOLATE, BC_INFLOW, BC_NAMES, BC_NOSLIP, BC_TANGENT,
-                   FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_STATE, MiniAeroError)
+                   FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_PRIMITIVES, MiniAeroError)
 
 __all__ = ["Options", "Parallel3DMesh", "MeshData", "Faces", "TimeSolverExplicitRK4", "HaloComm", "MiniAeroError",
            "ARITH_FAST", "ARITH_STRICT", "probe_roe_flux", "probe_viscous_flux", "probe_primitives",
@@ -247,7 +247,7 @@ class TimeSolverExplicitRK4:
 
     def field(self, which):
         shape = {FIELD_GRADIENT: (self.num_owned_cells, 5, 3), FIELD_LIMITER: (self.num_owned_cells, 5),
-                 FIELD_STAGE_STATE: (self.num_owned_cells, 5)}[which]
+                 FIELD_STAGE_PRIMITIVES: (self.num_owned_cells, 5)}[which]
         out = np.empty(shape, dtype=np.float64)
         _abi.check(self._lib.ma_solver_get_field(self._handle, which, out.ctypes.data))
         return out

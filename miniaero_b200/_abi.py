@@ -13,7 +13,7 @@ MA_OK = 0
 BC_EXTRAPOLATE, BC_TANGENT, BC_INFLOW, BC_NOSLIP = 0, 1, 2, 3
 BC_NAMES = {"Extrapolate": BC_EXTRAPOLATE, "Tangent": BC_TANGENT, "Inflow": BC_INFLOW, "NoSlip": BC_NOSLIP}
 ARITH_FAST, ARITH_STRICT = 0, 1
-FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_STATE = 0, 1, 2
+FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_PRIMITIVES = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

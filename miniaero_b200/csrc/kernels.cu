@@ -27,20 +27,51 @@ MA_DEV void load_state(const double *__restrict__ base, int stride, int c, doubl
   for (int k = 0; k < 5; ++k) v[k] = __ldg(base + (size_t)k * stride + c);
 }
 
+// Face geometry as the kernels see it.  STRICT keeps the caller's tangent and binormal (the reference
+// normalises and uses them, Roe_Flux.h:101-123); FAST needs only the area vector (see roe_flux_normal_only).
+#ifdef MA_STRICT
+#define MA_GEOM_XF 9
+struct FaceGeom {
+  double n[3], t[3], b[3];
+};
+MA_DEV void load_face_geom(const DevMesh &m, size_t NF, int j, FaceGeom &g) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    g.n[d] = __ldg(m.face_geom + (size_t)(0 + d) * NF + j);
+    g.t[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j);
+    g.b[d] = __ldg(m.face_geom + (size_t)(6 + d) * NF + j);
+  }
+}
+MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const FaceGeom &g, double (&flux)[5]) {
+  roe_flux(Vl, Vr, g.n, g.t, g.b, flux);
+}
+#else
+#define MA_GEOM_XF 3
+struct FaceGeom {
+  double n[3];
+};
+MA_DEV void load_face_geom(const DevMesh &m, size_t NF, int j, FaceGeom &g) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) g.n[d] = __ldg(m.face_geom + (size_t)d * NF + j);
+}
+MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const FaceGeom &g, double (&flux)[5]) {
+  roe_flux_normal_only(Vl, Vr, g.n, flux);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------------
+// V = primitives (rho, u, v, w, T) of the stage state, [5][stride], ghosts included.
 template <bool SECOND>
-__global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, const double *__restrict__ W,
+__global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, const double *__restrict__ V_,
                                                            double *__restrict__ grad, double *__restrict__ lim,
                                                            int tile_begin) {
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   const size_t NF = (size_t)m.n_tile_faces;
   for (int lc = threadIdx.x; lc < T.cell_count; lc += blockDim.x) {
     const int c = T.cell_start + lc;
-    double U[5], V[5];
-    load_state(W, m.stride, c, U);
-    compute_primitives(U, V);
+    double V[5];
+    load_state(V_, m.stride, c, V);
     const double vol = __ldg(m.cell_vol + c);
-    const double rvol = rcp(vol);
     double g[5][3];
     double mn[5], mx[5];
 #pragma unroll
@@ -62,18 +93,32 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
       for (int d = 0; d < 3; ++d) n[d] = __ldg(m.face_geom + (size_t)d * NF + j);
       if (r >= 0) {
         const int nb = side ? __ldg(m.face_left + j) : r;
-        double Un[5], Vn[5];
-        load_state(W, m.stride, nb, Un);
-        compute_primitives(Un, Vn);
+        double Vn[5];
+        load_state(V_, m.stride, nb, Vn);
+#ifdef MA_STRICT
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const double avg = 0.5 * (V[k] + Vn[k]);  // GreenGauss.h:117
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
-            const double q = div_by(avg * n[d], vol, rvol);
+            const double q = avg * n[d] / vol;
             g[k][d] += side ? -q : q;  // GreenGauss.h:130-131
           }
-          if (SECOND) {
+        }
+#else
+        // FAST: the 0.5 and 1/vol factors are applied once after the slot loop
+        const double sgn = side ? -1.0 : 1.0;
+        const double sn[3] = {sgn * n[0], sgn * n[1], sgn * n[2]};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const double sum = V[k] + Vn[k];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) g[k][d] = fma(sum, sn[d], g[k][d]);
+        }
+#endif
+        if (SECOND) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
             mn[k] = fmin(mn[k], fmin(Vn[k], V[k]));  // StencilLimiter.h:139-140,272-273
             mx[k] = fmax(mx[k], fmax(Vn[k], V[k]));
           }
@@ -81,8 +126,14 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
       } else {
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
+#ifdef MA_STRICT
 #pragma unroll
-          for (int d = 0; d < 3; ++d) g[k][d] += div_by(V[k] * n[d], vol, rvol);  // GreenGauss.h:186-216
+          for (int d = 0; d < 3; ++d) g[k][d] += V[k] * n[d] / vol;  // GreenGauss.h:186-216
+#else
+          const double two_v = 2.0 * V[k];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) g[k][d] = fma(two_v, n[d], g[k][d]);
+#endif
           if (SECOND) {
             mn[k] = fmin(mn[k], V[k]);
             mx[k] = fmax(mx[k], V[k]);
@@ -90,6 +141,15 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
         }
       }
     }
+#ifndef MA_STRICT
+    {
+      const double half_rvol = 0.5 * rcp(vol);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[k][d] *= half_rvol;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < 5; ++k)
 #pragma unroll
@@ -99,7 +159,17 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
       double xc[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
+#ifdef MA_STRICT
       double phi[5] = {1.0, 1.0, 1.0, 1.0, 1.0};  // StencilLimiter.h:308-311
+#else
+      double pN[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pD[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+      double dumax[5], dumin[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        dumax[k] = mx[k] - V[k];
+        dumin[k] = mn[k] - V[k];
+      }
+#endif
 #pragma unroll
       for (int s = 0; s < 6; ++s) {
         const int j = fj[s];
@@ -107,7 +177,7 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
         double dist = 0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          disp[d] = __ldg(m.face_geom + (size_t)(9 + d) * NF + j) - xc[d];  // StencilLimiter.h:425-433
+          disp[d] = __ldg(m.face_geom + (size_t)(MA_GEOM_XF + d) * NF + j) - xc[d];  // StencilLimiter.h:425-433
           dist += disp[d] * disp[d];
         }
 #pragma unroll
@@ -115,13 +185,25 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
           double dU = 0;
 #pragma unroll
           for (int d = 0; d < 3; ++d) dU += disp[d] * g[k][d];  // StencilLimiter.h:438-446
+#ifdef MA_STRICT
           const double dumax = mx[k] - V[k];
           const double dumin = mn[k] - V[k];
           phi[k] = fmin(phi[k], venkat_limit(dumax, dumin, dU, dist));  // StencilLimiter.h:451-455, 345-346
+#else
+          double N, D;
+          venkat_fraction(dumax[k], dumin[k], dU, dist, N, D);
+          venkat_fraction_min(N, D, pN[k], pD[k]);
+#endif
         }
       }
 #pragma unroll
-      for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = phi[k];
+      for (int k = 0; k < 5; ++k) {
+#ifdef MA_STRICT
+        lim[(size_t)k * m.stride + c] = phi[k];
+#else
+        lim[(size_t)k * m.stride + c] = quot(pN[k], pD[k]);
+#endif
+      }
     }
   }
 }
@@ -133,34 +215,27 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   const size_t NF = (size_t)m.n_tile_faces;
   const int FS = m.flux_smem_stride;
-  const double *__restrict__ W = a.W;
+  const double *__restrict__ V_ = a.V;
 
   // ---- phase 1: one flux per tile face
   for (int e = threadIdx.x; e < T.face_count; e += blockDim.x) {
     const int j = T.face_start + e;
     const int l = __ldg(m.face_left + j);
     const int r = __ldg(m.face_right + j);
-    double n[3], t[3], b[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      n[d] = __ldg(m.face_geom + (size_t)(0 + d) * NF + j);
-      t[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j);
-      b[d] = __ldg(m.face_geom + (size_t)(6 + d) * NF + j);
-    }
-    double Ul[5], Vl[5], flux[5];
-    load_state(W, m.stride, l, Ul);
-    compute_primitives(Ul, Vl);
+    FaceGeom G;
+    load_face_geom(m, NF, j, G);
+    double Vl[5], flux[5];
+    load_state(V_, m.stride, l, Vl);
     if (r >= 0) {
       // interior face: Flux.h:89-160
-      double Ur[5], Vr[5];
-      load_state(W, m.stride, r, Ur);
-      compute_primitives(Ur, Vr);
+      double Vr[5];
+      load_state(V_, m.stride, r, Vr);
       double gf[5][3];
       if (SECOND) {
         double dl[3], dr[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const double xf = __ldg(m.face_geom + (size_t)(9 + d) * NF + j);
+          const double xf = __ldg(m.face_geom + (size_t)(MA_GEOM_XF + d) * NF + j);
           dl[d] = xf - __ldg(m.cell_xyz + (size_t)d * m.stride + l);
           dr[d] = xf - __ldg(m.cell_xyz + (size_t)d * m.stride + r);
         }
@@ -186,12 +261,12 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
             gf[k][d] = 0.5 * (__ldg(a.grad + (size_t)(k * 3 + d) * m.stride + l) +
                               __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + r));
       }
-      roe_flux(Vl, Vr, n, t, b, flux);
+      face_roe_flux(Vl, Vr, G, flux);
       if (VISCOUS) {
         double Vf[5], vflux[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) Vf[k] = 0.5 * (Vl[k] + Vr[k]);  // Flux.h:142-143
-        viscous_flux(gf, Vf, n, vflux);
+        viscous_flux(gf, Vf, G.n, vflux);
 #pragma unroll
         for (int k = 0; k < 5; ++k) flux[k] -= vflux[k];
       }
@@ -209,17 +284,17 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
         for (int k = 0; k < 5; ++k) Ui[k] = m.inflow[k];
         compute_primitives(Ui, Vr);
       } else {  // Tangent_BC.h:82-101, NoSlip_BC.h:96-112
-        mirror_state(Vl, n, Vr, area_norm);
+        mirror_state(Vl, G.n, Vr, area_norm);
       }
-      roe_flux(Vl, Vr, n, t, b, flux);
+      face_roe_flux(Vl, Vr, G, flux);
       if (type == 3) {  // NoSlip_BC.h:114-139 — viscous wall flux regardless of options.viscous
         double xf[3], xc[3], vflux[5];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          xf[d] = __ldg(m.face_geom + (size_t)(9 + d) * NF + j);
+          xf[d] = __ldg(m.face_geom + (size_t)(MA_GEOM_XF + d) * NF + j);
           xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + l);
         }
-        noslip_viscous_flux(Vl, n, area_norm, xf, xc, vflux);
+        noslip_viscous_flux(Vl, G.n, area_norm, xf, xc, vflux);
 #pragma unroll
         for (int k = 0; k < 5; ++k) flux[k] -= vflux[k];  // slot = -iflux + vflux == -(iflux - vflux)
       }
@@ -229,10 +304,14 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
   }
   __syncthreads();
 
-  // ---- phase 2: slot-ordered gather, residual, RK update
+  // ---- phase 2: slot-ordered gather, residual, RK update; the next stage state is stored as primitives
   for (int lc = threadIdx.x; lc < T.cell_count; lc += blockDim.x) {
     const int c = T.cell_start + lc;
+#ifdef MA_STRICT
     const double dtv = a.dt / __ldg(m.cell_vol + c);  // Flux.h:224-225: dt_/volume_(i) * flux
+#else
+    const double dtv = a.dt * rcp(__ldg(m.cell_vol + c));
+#endif
     double R[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
@@ -245,24 +324,44 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
         R[k] = R[k] + dtv * (right ? f : -f);  // Flux.h:172-178: left slot holds -flux, right slot +flux
       }
     }
+    double Wn[5];  // conservative state the next stage is evaluated at (or the new solution)
     if (a.kind == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double w = W[(size_t)k * m.stride + c];
-        a.AccOut[(size_t)k * m.stride + c] = w + a.beta * R[k];
-        a.Wnext[(size_t)k * m.stride + c] = w + a.alpha_next * R[k];
+        const double w = a.Un[(size_t)k * m.stride + c];
+        a.Acc[(size_t)k * m.stride + c] = w + a.beta * R[k];
+        Wn[k] = w + a.alpha_next * R[k];
       }
     } else if (a.kind == 1) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        a.AccOut[(size_t)k * m.stride + c] = a.AccIn[(size_t)k * m.stride + c] + a.beta * R[k];
-        a.Wnext[(size_t)k * m.stride + c] = a.Un[(size_t)k * m.stride + c] + a.alpha_next * R[k];
+        a.Acc[(size_t)k * m.stride + c] = a.Acc[(size_t)k * m.stride + c] + a.beta * R[k];
+        Wn[k] = a.Un[(size_t)k * m.stride + c] + a.alpha_next * R[k];
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) a.Wnext[(size_t)k * m.stride + c] = a.AccIn[(size_t)k * m.stride + c] + a.beta * R[k];
+      for (int k = 0; k < 5; ++k) {
+        Wn[k] = a.Acc[(size_t)k * m.stride + c] + a.beta * R[k];
+        a.Un[(size_t)k * m.stride + c] = Wn[k];
+      }
     }
+    double Vn[5];
+    compute_primitives(Wn, Vn);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a.Vnext[(size_t)k * m.stride + c] = Vn[k];
   }
+}
+
+// U (conservative, owned cells) -> V (primitives): after initial conditions / set_solution
+__global__ void primitives_kernel(const DevMesh m, const double *__restrict__ Un, double *__restrict__ V) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m.n_owned) return;
+  double U[5], P[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) U[k] = Un[(size_t)k * m.stride + c];
+  compute_primitives(U, P);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) V[(size_t)k * m.stride + c] = P[k];
 }
 
 __global__ void initial_conditions_kernel(const DevMesh m, double *__restrict__ Un, int sod, double midx,
@@ -287,10 +386,16 @@ __global__ void probe_roe_kernel(int n, const double *vl, const double *vr, cons
                                  const double *bb, double *flux) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double Vl[5], Vr[5], N[3], Tt[3], B[3], F[5];
+  double Vl[5], Vr[5], F[5];
+  FaceGeom G;
   for (int k = 0; k < 5; ++k) Vl[k] = vl[5 * i + k], Vr[k] = vr[5 * i + k];
-  for (int d = 0; d < 3; ++d) N[d] = nn[3 * i + d], Tt[d] = tt[3 * i + d], B[d] = bb[3 * i + d];
-  roe_flux(Vl, Vr, N, Tt, B, F);
+  for (int d = 0; d < 3; ++d) {
+    G.n[d] = nn[3 * i + d];
+#ifdef MA_STRICT
+    G.t[d] = tt[3 * i + d], G.b[d] = bb[3 * i + d];
+#endif
+  }
+  face_roe_flux(Vl, Vr, G, F);  // the production face flux of this arithmetic mode
   for (int k = 0; k < 5; ++k) flux[5 * i + k] = F[k];
 }
 __global__ void probe_viscous_kernel(int n, const double *g, const double *v, const double *a, double *vf) {
@@ -316,7 +421,14 @@ __global__ void probe_primitives_kernel(int n, const double *u, double *v) {
 __global__ void probe_venkat_kernel(int n, const double *dmax, const double *dmin, const double *du,
                                     const double *dx3, double *phi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) phi[i] = venkat_limit(dmax[i], dmin[i], du[i], dx3[i]);
+  if (i >= n) return;
+#ifdef MA_STRICT
+  phi[i] = venkat_limit(dmax[i], dmin[i], du[i], dx3[i]);
+#else
+  double N, D;
+  venkat_fraction(dmax[i], dmin[i], du[i], dx3[i], N, D);
+  phi[i] = quot(N, D);
+#endif
 }
 __global__ void probe_vanalbada_kernel(int n, const double *dmax, const double *dmin, const double *du, double *phi) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,13 +436,13 @@ __global__ void probe_vanalbada_kernel(int n, const double *dmax, const double *
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------
-cudaError_t launch_grad_limiter(const DevMesh &m, const double *W, double *grad, double *lim, bool second,
+cudaError_t launch_grad_limiter(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                 int tile_begin, int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
   if (second)
-    grad_limiter_kernel<true><<<ntiles, threads, 0, st>>>(m, W, grad, lim, tile_begin);
+    grad_limiter_kernel<true><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
   else
-    grad_limiter_kernel<false><<<ntiles, threads, 0, st>>>(m, W, grad, lim, tile_begin);
+    grad_limiter_kernel<false><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
   return cudaGetLastError();
 }
 
@@ -359,6 +471,12 @@ cudaError_t launch_flux_rk(const DevMesh &m, const StageArgs &a, bool second, bo
     flux_rk_kernel<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else
     flux_rk_kernel<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_primitives(const DevMesh &m, const double *Un, double *V, cudaStream_t st) {
+  const int threads = 256;
+  primitives_kernel<<<(m.n_owned + threads - 1) / threads, threads, 0, st>>>(m, Un, V);
   return cudaGetLastError();
 }
 

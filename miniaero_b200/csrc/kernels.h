@@ -21,21 +21,20 @@ struct DevMesh {
   const double *cell_xyz;              // [3][stride]
   const double *cell_vol;              // [stride]
   const uint16_t *slot_face;           // [6][slot_stride]
-  const double *face_geom;             // [12][n_tile_faces]: normal, tangent, binormal, centroid
+  const double *face_geom;             // STRICT [12][n_tile_faces]: normal, tangent, binormal, centroid; FAST [6]: normal, centroid
   const int *face_left, *face_right;   // [n_tile_faces]
   double inflow[5];                    // TimeSolverExplicitRK4.h:218-223
 };
 
 struct StageArgs {
-  const double *W;     // stage state, read for every cell a tile touches   ("solution_temp")
-  const double *Un;    // state at the start of the step                     ("solution_n")
-  const double *AccIn; // running RK sum                                     ("solution_np1")
-  double *AccOut;
-  double *Wnext;       // next stage state; for the last stage the new Un
+  const double *V;     // primitives (rho,u,v,w,T) of the stage state, every cell a tile touches ("solution_temp")
+  double *Vnext;       // primitives of the next stage state (for the last stage: of the new solution)
+  double *Un;          // conservative state at the start of the step ("solution_n"); written by the last stage
+  double *Acc;         // running RK sum ("solution_np1"), updated in place
   const double *grad;  // [15][stride]
   const double *lim;   // [5][stride]
   double dt, alpha_next, beta;
-  int kind;            // 0 first stage (W == Un == Acc), 1 middle, 2 last
+  int kind;            // 0 first stage (stage state == Un), 1 middle, 2 last
 };
 
 }  // namespace ma
@@ -43,12 +42,14 @@ struct StageArgs {
 #define MA_DECLARE_KERNEL_API(NS)                                                                                    \
   namespace NS {                                                                                                     \
   /* GreenGauss.h:51-270 + StencilLimiter.h:56-500 fused, cell-centric, tiles [tile_begin, tile_begin+ntiles) */     \
-  cudaError_t launch_grad_limiter(const ma::DevMesh &m, const double *W, double *grad, double *lim, bool second,     \
+  cudaError_t launch_grad_limiter(const ma::DevMesh &m, const double *V, double *grad, double *lim, bool second,     \
                                   int tile_begin, int ntiles, int threads, cudaStream_t st);                         \
   /* Flux.h:52-229 + the four *_BC.h + TimeSolverExplicitRK4.h:106-128 fused */                                      \
   cudaError_t launch_flux_rk(const ma::DevMesh &m, const ma::StageArgs &a, bool second, bool viscous,                \
                              int tile_begin, int ntiles, int threads, cudaStream_t st);                              \
   cudaError_t flux_rk_prepare(int smem_bytes);                                                                       \
+  /* GasModel.h:70-90 over the owned cells: conservative Un -> primitives V */                                       \
+  cudaError_t launch_primitives(const ma::DevMesh &m, const double *Un, double *V, cudaStream_t st);                 \
   /* Initial_Conditions.h:38-133 */                                                                                  \
   cudaError_t launch_initial_conditions(const ma::DevMesh &m, double *Un, int problem_type, double midx,             \
                                         cudaStream_t st);                                                            \

@@ -27,7 +27,7 @@ inline int round_up(long v, int m) { return (int)(((v + m - 1) / m) * m); }
 
 }  // namespace
 
-int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], HostLayout &L) {
+int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tangents, HostLayout &L) {
   const int n_owned = mesh.num_owned_cells, n_ghost = mesh.num_ghosts;
   const long n_cells = (long)n_owned + n_ghost;
   if (n_owned <= 0 || n_ghost < 0) return ma_set_error(MA_ERR_INVALID, "mesh: num_owned_cells must be > 0");
@@ -52,6 +52,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], HostLayout &L) 
   L = HostLayout();
   L.n_owned = n_owned;
   L.n_ghost = n_ghost;
+  L.geom_components = with_tangents ? 12 : 6;
   L.stride = round_up(n_cells, 32);
   for (int d = 0; d < 3; ++d) L.tile_dims[d] = tile_dims_in[d] > 0 ? tile_dims_in[d] : 8;
   L.max_tile_cells = L.tile_dims[0] * L.tile_dims[1] * L.tile_dims[2];
@@ -304,10 +305,12 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], HostLayout &L) 
   L.n_tile_faces = fstart[n_tiles];
   L.n_tile_faces_real = real;
   const size_t NF = (size_t)L.n_tile_faces;
-  L.face_geom.assign(12 * NF, 0.0);
+  L.face_geom.assign((size_t)L.geom_components * NF, 0.0);
+  const int GX = with_tangents ? 9 : 3;  // first centroid component
+  double frame_err = 0.0;
   L.face_left.assign(NF, 0);
   L.face_right.assign(NF, 0);
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
     int e = 0;
@@ -320,11 +323,27 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], HostLayout &L) 
         const FaceSrc src = face_src(ref);
         const size_t j = (size_t)T.face_start + e;
         const size_t fi = (size_t)src.index;
+        const double *fn = src.f->face_normal + 3 * fi, *ft = src.f->face_tangent + 3 * fi,
+                     *fb = src.f->face_binormal + 3 * fi;
         for (int d = 0; d < 3; ++d) {
-          L.face_geom[(0 + d) * NF + j] = src.f->face_normal[3 * fi + d];
-          L.face_geom[(3 + d) * NF + j] = src.f->face_tangent[3 * fi + d];
-          L.face_geom[(6 + d) * NF + j] = src.f->face_binormal[3 * fi + d];
-          L.face_geom[(9 + d) * NF + j] = src.f->coordinates[3 * fi + d];
+          L.face_geom[(0 + d) * NF + j] = fn[d];
+          if (with_tangents) {
+            L.face_geom[(3 + d) * NF + j] = ft[d];
+            L.face_geom[(6 + d) * NF + j] = fb[d];
+          }
+          L.face_geom[(GX + d) * NF + j] = src.f->coordinates[3 * fi + d];
+        }
+        {  // how far (n/|n|, t, b/|n|) is from orthonormal (FAST arithmetic relies on it, Face.C:81-96)
+          const double a2 = fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2];
+          const double an = std::sqrt(a2);
+          const double tt = ft[0] * ft[0] + ft[1] * ft[1] + ft[2] * ft[2];
+          const double bb = (fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]) / a2;
+          const double nt = (fn[0] * ft[0] + fn[1] * ft[1] + fn[2] * ft[2]) / an;
+          const double nb = (fn[0] * fb[0] + fn[1] * fb[1] + fn[2] * fb[2]) / a2;
+          const double tb = (ft[0] * fb[0] + ft[1] * fb[1] + ft[2] * fb[2]) / an;
+          double err = std::max(std::fabs(tt - 1.0), std::fabs(bb - 1.0));
+          err = std::max(err, std::max(std::fabs(nt), std::max(std::fabs(nb), std::fabs(tb))));
+          if (!(err <= frame_err)) frame_err = (err == err) ? err : 1e300;
         }
         L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
         if (src.bc_type >= 0) {
@@ -344,6 +363,8 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], HostLayout &L) 
       }
     }
   }
+
+  L.max_frame_error = frame_err;
 
   // ---- 6. halo lists (renumbered), grouped by peer
   if (n_ghost > 0) {

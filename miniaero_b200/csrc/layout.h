@@ -43,7 +43,10 @@ struct HostLayout {
   int slot_stride = 0;
 
   // tile-packed face SoA, length n_tile_faces each: geometry component g of face j at geom[g*n_tile_faces + j]
-  // g: 0-2 normal, 3-5 tangent, 6-8 binormal, 9-11 centroid
+  // with_tangents: g = 0-2 normal, 3-5 tangent, 6-8 binormal, 9-11 centroid (STRICT arithmetic);
+  // otherwise     : g = 0-2 normal, 3-5 centroid (FAST arithmetic never reads tangent / binormal)
+  int geom_components = 12;
+  double max_frame_error = 0.0;  // worst deviation of (n^, t, b/|a|) from an orthonormal frame over all faces
   std::vector<double> face_geom;
   std::vector<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
 
@@ -53,6 +56,6 @@ struct HostLayout {
 };
 
 // Returns MA_OK or sets the error text.  tile_dims: requested cells per tile per direction.
-int build_layout(const ma_mesh &mesh, const int tile_dims[3], HostLayout &L);
+int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L);
 
 }  // namespace ma

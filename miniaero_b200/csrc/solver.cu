@@ -99,11 +99,12 @@ struct ma_solver {
   double *d_xyz = nullptr, *d_vol = nullptr, *d_geom = nullptr;
   uint16_t *d_slot = nullptr;
   int *d_fl = nullptr, *d_fr = nullptr, *d_old2new = nullptr, *d_send_ids = nullptr, *d_recv_ids = nullptr;
-  double *d_Un = nullptr, *d_Acc = nullptr, *d_Wa = nullptr, *d_Wb = nullptr, *d_grad = nullptr, *d_lim = nullptr;
+  double *d_Un = nullptr, *d_Acc = nullptr, *d_V[2] = {nullptr, nullptr}, *d_grad = nullptr, *d_lim = nullptr;
+  int vcur = 0;  // d_V[vcur] holds the primitives of the state the next stage is evaluated at
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr, *d_stage = nullptr;
   size_t stage_elems = 0;
   size_t device_bytes = 0;
-  const double *last_stage_state = nullptr;
+  const double *last_stage_prims = nullptr;
   // execution
   cudaStream_t st = nullptr, cs = nullptr;
   bool own_stream = false, own_cs = false;
@@ -130,13 +131,14 @@ struct Api {
   decltype(&ma_fast::launch_flux_rk) flux;
   decltype(&ma_fast::flux_rk_prepare) prepare;
   decltype(&ma_fast::launch_initial_conditions) ic;
+  decltype(&ma_fast::launch_primitives) prims;
 };
 Api api_of(bool strict) {
   if (strict)
     return {&ma_strict::launch_grad_limiter, &ma_strict::launch_flux_rk, &ma_strict::flux_rk_prepare,
-            &ma_strict::launch_initial_conditions};
+            &ma_strict::launch_initial_conditions, &ma_strict::launch_primitives};
   return {&ma_fast::launch_grad_limiter, &ma_fast::launch_flux_rk, &ma_fast::flux_rk_prepare,
-          &ma_fast::launch_initial_conditions};
+          &ma_fast::launch_initial_conditions, &ma_fast::launch_primitives};
 }
 
 int check_device(int device) {
@@ -245,32 +247,31 @@ int wait_state_exchange(ma_solver *S) {
 int run_stage(ma_solver *S, const Api &K, int k) {
   static const double alpha[4] = {0.0, 1.0 / 2.0, 1.0 / 2.0, 1.0};                  // TimeSolverExplicitRK4.h:188-191
   static const double beta[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};       // :192-195
-  const double *W = (k == 0) ? S->d_Un : ((k & 1) ? S->d_Wa : S->d_Wb);
-  double *Wnext = (k == 0) ? S->d_Wa : (k == 1) ? S->d_Wb : (k == 2) ? S->d_Wa : S->d_Un;
+  const double *V = S->d_V[S->vcur];
+  double *Vnext = S->d_V[S->vcur ^ 1];
   ma::StageArgs a;
-  a.W = W;
+  a.V = V;
+  a.Vnext = Vnext;
   a.Un = S->d_Un;
-  a.AccIn = S->d_Acc;
-  a.AccOut = S->d_Acc;
-  a.Wnext = Wnext;
+  a.Acc = S->d_Acc;
   a.grad = S->d_grad;
   a.lim = S->d_lim;
   a.dt = S->opt.dt;
   a.alpha_next = (k < 3) ? alpha[k + 1] : 0.0;
   a.beta = beta[k];
   a.kind = (k == 0) ? 0 : (k == 3) ? 2 : 1;
-  S->last_stage_state = W;
+  S->last_stage_prims = V;
   const int nint = S->n_ghost ? S->n_interior_tiles : S->n_tiles;
   const int nbnd = S->n_tiles - nint;
 
   if (S->need_grad) {
     {
       ProfScope p(S, &S->tm.grad_seconds);
-      MA_CUDA_TRY(K.grad(S->dm, W, S->d_grad, S->d_lim, S->second, 0, nint, S->grad_threads, S->st));
+      MA_CUDA_TRY(K.grad(S->dm, V, S->d_grad, S->d_lim, S->second, 0, nint, S->grad_threads, S->st));
       S->tm.kernel_launches += nint > 0;
       int rc = wait_state_exchange(S);
       if (rc) return rc;
-      MA_CUDA_TRY(K.grad(S->dm, W, S->d_grad, S->d_lim, S->second, nint, nbnd, S->grad_threads, S->st));
+      MA_CUDA_TRY(K.grad(S->dm, V, S->d_grad, S->d_lim, S->second, nint, nbnd, S->grad_threads, S->st));
       S->tm.kernel_launches += nbnd > 0;
     }
     if (S->n_ghost) {  // gradient (+ limiter) halo: GreenGauss.h:324-338, StencilLimiter.h:618-631
@@ -298,7 +299,8 @@ int run_stage(ma_solver *S, const Api &K, int k) {
     MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
     S->tm.kernel_launches += nbnd > 0;
   }
-  return start_state_exchange(S, Wnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
+  S->vcur ^= 1;
+  return start_state_exchange(S, Vnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
 }
 
 int ensure_staging(ma_solver *S, size_t elems) {
@@ -353,7 +355,7 @@ void ma_solver_destroy(ma_solver *S) {
   if (S->st) cudaStreamSynchronize(S->st);
   if (S->cs) cudaStreamSynchronize(S->cs);
   void *ptrs[] = {S->d_tiles, S->d_xyz,  S->d_vol,  S->d_geom, S->d_slot,    S->d_fl,      S->d_fr,   S->d_old2new,
-                  S->d_send_ids, S->d_recv_ids, S->d_Un, S->d_Acc, S->d_Wa, S->d_Wb, S->d_grad, S->d_lim,
+                  S->d_send_ids, S->d_recv_ids, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
                   S->d_sendbuf, S->d_recvbuf, S->d_stage};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -389,7 +391,12 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   int td[3];
   for (int d = 0; d < 3; ++d) td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : 8;
   ma::HostLayout L;
-  rc = ma::build_layout(*mesh, td, L);
+  rc = ma::build_layout(*mesh, td, cfg.arith == MA_ARITH_STRICT, L);
+  if (rc) return rc;
+  if (cfg.arith == MA_ARITH_FAST && !(L.max_frame_error <= 1e-9))
+    return ma_set_error(MA_ERR_INVALID,
+                        "MA_ARITH_FAST needs face (normal, tangent, binormal) triples that are orthogonal with unit tangent and "
+                        "|binormal| = |normal| (as Face.C:81-96 builds them); use MA_ARITH_STRICT for arbitrary frames");
   if (rc) return rc;
 
   ma_solver *S = new ma_solver();
@@ -461,7 +468,7 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   MA_TRY(dev_upload(&S->d_send_ids, L.send_ids, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_recv_ids, L.recv_ids, &S->device_bytes));
   const size_t sv = (size_t)5 * S->stride;
-  double **states[] = {&S->d_Un, &S->d_Acc, &S->d_Wa, &S->d_Wb};
+  double **states[] = {&S->d_Un, &S->d_Acc, &S->d_V[0], &S->d_V[1]};
   for (double **p : states) {
     MA_TRY(dev_alloc(p, sv, &S->device_bytes));
     MA_CU(cudaMemset(*p, 0, sv * sizeof(double)));  // ghosts start at zero like the reference's Views
@@ -520,9 +527,12 @@ int ma_solver_initialize(ma_solver *S) {
   MA_CUDA_TRY(cudaMemsetAsync(S->d_Un, 0, sv, S->st));
   const double midx = S->opt.lx / 2.0;  // TimeSolverExplicitRK4.h:217
   MA_CUDA_TRY(K.ic(S->dm, S->d_Un, S->opt.problem_type, midx, S->st));
+  S->vcur = 0;
+  MA_CUDA_TRY(cudaMemsetAsync(S->d_V[0], 0, sv, S->st));
+  MA_CUDA_TRY(K.prims(S->dm, S->d_Un, S->d_V[0], S->st));
   S->sim_time = 0.0;
   S->time_it = 0;
-  int rc = start_state_exchange(S, S->d_Un);
+  int rc = start_state_exchange(S, S->d_V[0]);
   if (rc) return rc;
   return MA_OK;
 }
@@ -607,7 +617,8 @@ int ma_solver_set_solution(ma_solver *S, const double *host) {
   caller_to_soa_kernel<<<(unsigned)((elems + threads - 1) / threads), threads, 0, S->st>>>(
       S->d_stage, S->stride, 5, S->n_owned, S->d_old2new, S->d_Un);
   MA_CUDA_TRY(cudaGetLastError());
-  return start_state_exchange(S, S->d_Un);
+  MA_CUDA_TRY(api_of(S->strict).prims(S->dm, S->d_Un, S->d_V[S->vcur], S->st));
+  return start_state_exchange(S, S->d_V[S->vcur]);
 }
 
 int ma_solver_get_field(ma_solver *S, int field, double *host) {
@@ -619,9 +630,9 @@ int ma_solver_get_field(ma_solver *S, int field, double *host) {
     case MA_FIELD_LIMITER:
       if (!S->d_lim) return ma_set_error(MA_ERR_INVALID, "limiters are only computed for second-order runs");
       return download_field(S, S->d_lim, 5, host);
-    case MA_FIELD_STAGE_STATE:
-      if (!S->last_stage_state) return ma_set_error(MA_ERR_INVALID, "no RK stage has run yet");
-      return download_field(S, S->last_stage_state, 5, host);
+    case MA_FIELD_STAGE_PRIMITIVES:
+      if (!S->last_stage_prims) return ma_set_error(MA_ERR_INVALID, "no RK stage has run yet");
+      return download_field(S, S->last_stage_prims, 5, host);
     default:
       return ma_set_error(MA_ERR_INVALID, "unknown field");
   }
