@@ -16,6 +16,16 @@
 #include "kernels.h"
 #include "physics.cuh"
 
+// launch bounds (max threads per CTA, min resident CTAs per SM) of the two stage kernels
+#ifndef MA_GRAD_THREADS
+#define MA_GRAD_THREADS 256
+#define MA_GRAD_MINB 1
+#endif
+#ifndef MA_FLUX_THREADS
+#define MA_FLUX_THREADS 256
+#define MA_FLUX_MINB 1
+#endif
+
 namespace MA_NS {
 
 using ma::DevMesh;
@@ -62,7 +72,7 @@ MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const Fa
 // ------------------------------------------------------------------------------------------------------
 // V = primitives (rho, u, v, w, T) of the stage state, [5][stride], ghosts included.
 template <bool SECOND>
-__global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, const double *__restrict__ V_,
+__global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_kernel(const DevMesh m, const double *__restrict__ V_,
                                                            double *__restrict__ grad, double *__restrict__ lim,
                                                            int tile_begin) {
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
@@ -85,7 +95,7 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
     for (int s = 0; s < 6; ++s) {  // slot order == the reference's gather order (GreenGauss.h:255-267)
       const unsigned sf = m.slot_face[(size_t)s * m.slot_stride + c];
       const int side = sf >> 15;
-      const int j = T.face_start + (int)(sf & 0x7fffu);
+      const int j = T.face_start + (int)(sf & 0x3fffu);
       fj[s] = j;
       const int r = __ldg(m.face_right + j);
       double n[3];
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(256) grad_limiter_kernel(const DevMesh m, cons
 
 // ------------------------------------------------------------------------------------------------------
 template <bool SECOND, bool VISCOUS>
-__global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
+__global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
   extern __shared__ double sflux[];
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   const size_t NF = (size_t)m.n_tile_faces;
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       const unsigned sf = m.slot_face[(size_t)s * m.slot_stride + c];
-      const int e = (int)(sf & 0x7fffu);
+      const int e = (int)(sf & 0x3fffu);
       const bool right = (sf >> 15) != 0;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
@@ -351,6 +361,336 @@ __global__ void __launch_bounds__(256) flux_rk_kernel(const DevMesh m, const Sta
     for (int k = 0; k < 5; ++k) a.Vnext[(size_t)k * m.stride + c] = Vn[k];
   }
 }
+
+
+#ifndef MA_STRICT
+// ======================================================================================================
+// FAST tile kernels: cell-block tiles staged in shared memory.
+//
+// Every global load of cell data is issued by a thread that owns a whole cell (own cells: coalesced SoA
+// reads with no index indirection; outside cells of cut faces: one gather per cut face), so the per-face
+// gather of 2 x 28 doubles of the reference's compute_face_flux (Flux.h:89-132) never happens.
+// ======================================================================================================
+
+// ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
+// phase 0: primitives of the tile's cells and of the outside cells of its cut faces -> sV[5][LS]
+// phase 1: thread per cell, neighbours read from shared memory through the tile-local face table
+template <bool SECOND>
+__global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB)
+    grad_limiter_tile_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
+                             double *__restrict__ lim, int tile_begin) {
+  extern __shared__ double smem[];
+  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
+  const size_t NF = (size_t)m.n_tile_faces;
+  const int LS = m.local_smem_stride;
+  const int nc = T.cell_count;
+  const int nl = nc + (T.face_count - T.cut_start);
+  double *sV = smem;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+    const int c = i < nc ? T.cell_start + i : __ldg(m.tile_halo + T.halo_start + (i - nc));
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sV[k * LS + i] = __ldg(V_ + (size_t)k * m.stride + c);
+  }
+  __syncthreads();
+
+  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
+    const int c = T.cell_start + lc;
+    double V[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) V[k] = sV[k * LS + lc];
+    const double vol = __ldg(m.cell_vol + c);
+    double g[5][3], mn[5], mx[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      g[k][0] = g[k][1] = g[k][2] = 0;
+      mn[k] = mx[k] = V[k];  // min/max over {cell, face neighbours} (StencilLimiter.h:139-140, 272-273)
+    }
+    unsigned sfs[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) sfs[s] = m.slot_face[(size_t)s * m.slot_stride + c];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const unsigned sf = sfs[s];
+      const int side = sf >> 15;
+      const int j = T.face_start + (int)(sf & 0x3fffu);
+      const double sgn = side ? -1.0 : 1.0;
+      double sn[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sn[d] = sgn * __ldg(m.face_geom + (size_t)d * NF + j);
+      if (!(sf & 0x4000u)) {
+        const unsigned lr = __ldg(m.face_lr + j);
+        const int nb = side ? (int)(lr & 0xffffu) : (int)(lr >> 16);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const double vn = sV[k * LS + nb];
+          const double sum = V[k] + vn;  // 2 x GreenGauss.h:117; the 0.5/vol factor is applied after the loop
+#pragma unroll
+          for (int d = 0; d < 3; ++d) g[k][d] = fma(sum, sn[d], g[k][d]);
+          if (SECOND) {
+            mn[k] = fmin(mn[k], vn);
+            mx[k] = fmax(mx[k], vn);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const double two_v = 2.0 * V[k];  // GreenGauss.h:186-216
+#pragma unroll
+          for (int d = 0; d < 3; ++d) g[k][d] = fma(two_v, sn[d], g[k][d]);
+        }
+      }
+    }
+    {
+      const double half_rvol = 0.5 * rcp(vol);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          g[k][d] *= half_rvol;
+          grad[(size_t)(k * 3 + d) * m.stride + c] = g[k][d];
+        }
+    }
+    if (SECOND) {
+      double xc[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
+      double pN[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pD[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+      double dumax[5], ndumin[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        dumax[k] = mx[k] - V[k];
+        ndumin[k] = V[k] - mn[k];
+      }
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        const int j = T.face_start + (int)(sfs[s] & 0x3fffu);
+        double disp[3];
+        double dist = 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          disp[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j) - xc[d];  // StencilLimiter.h:425-433
+          dist = fma(disp[d], disp[d], dist);
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const double dU = disp[0] * g[k][0] + disp[1] * g[k][1] + disp[2] * g[k][2];  // StencilLimiter.h:438-446
+          // VenkatLimiter.h:45-73 with a = |du|, mm = |dumax| or |dumin| by the sign of du and the common factor
+          // du cancelled: phi = (mm^2 + eps2 + 2 a mm) / (mm^2 + eps2 + a (2a + mm)); phi -> 1 as a -> 0
+          const double a = fabs(dU);
+          const double mm = dU > 0.0 ? dumax[k] : ndumin[k];
+          const double base = fma(mm, mm, dist);
+          const double a2 = a + a;
+          const double N = fma(a2, mm, base);
+          const double D = fma(a, a2 + mm, base);
+          venkat_fraction_min(N, D, pN[k], pD[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = quot(pN[k], pD[k]);
+    }
+  }
+}
+
+// ---- sweep 2: face fluxes + slot-ordered gather + RK stage update -----------------------------------
+// Shared memory S[NC][FS] (component-major, one column per tile face):
+//   phase A  thread per cell (own cells, then the outside cell of every cut face): loads the cell's record
+//            (V 5, grad 15, lim 5, xyz 3) once and, for each of its faces in the tile, stores that side's
+//            limited-extrapolated primitives (Flux.h:109-132) and — viscous — its half of the face stress:
+//            q_i = sum_j tau_ij(grad) a_j, h = grad(T).a  (Viscous_Flux.h:65-98 is linear in the gradient, and
+//            the face gradient is the plain average of the two cell gradients, Flux.h:146-149)
+//   phase B  thread per face: Roe flux of the two staged states (+ viscous flux from the staged halves), or
+//            the boundary-condition flux; the result overwrites the face's column
+//   phase C  thread per cell: gather of the six face fluxes in slot order (Flux.h:216-227), RK update
+template <bool SECOND, bool VISCOUS>
+__global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB)
+    flux_rk_tile_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
+  extern __shared__ double S[];
+  constexpr int SIDE = VISCOUS ? 9 : 5;  // components per side: V'[5] (+ q[3], h)
+  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
+  const size_t NF = (size_t)m.n_tile_faces;
+  const int FS = m.flux_smem_stride;
+  const int nc = T.cell_count;
+  const int njobs = nc + (T.face_count - T.cut_start);
+
+  // ---- phase A
+  for (int i = threadIdx.x; i < njobs; i += blockDim.x) {
+    const bool own = i < nc;
+    const int c = own ? T.cell_start + i : __ldg(m.tile_halo + T.halo_start + (i - nc));
+    double V[5], lm[5], xc[3], g[5][3];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) V[k] = __ldg(a.V + (size_t)k * m.stride + c);
+    if (SECOND || VISCOUS) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[k][d] = __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + c);
+    }
+    if (SECOND) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) lm[k] = __ldg(a.lim + (size_t)k * m.stride + c);
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
+    double txx = 0, tyy = 0, tzz = 0, txy = 0, txz = 0, tyz = 0;
+    if (VISCOUS) {  // tau_ij = S_ij - delta_ij div/3 (Viscous_Flux.h:80-90)
+      const double third_div = (g[1][0] + g[2][1] + g[3][2]) * (1.0 / 3.0);
+      txx = g[1][0] - third_div, tyy = g[2][1] - third_div, tzz = g[3][2] - third_div;
+      txy = 0.5 * (g[1][1] + g[2][0]), txz = 0.5 * (g[1][2] + g[3][0]), tyz = 0.5 * (g[2][2] + g[3][1]);
+    }
+    unsigned sfs[6];
+    int nslots = 1;
+    if (own) {
+      nslots = 6;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) sfs[s] = m.slot_face[(size_t)s * m.slot_stride + c];
+    } else {
+      const int e = T.cut_start + (i - nc);
+      const unsigned lr = __ldg(m.face_lr + T.face_start + e);
+      sfs[0] = (unsigned)e | (((lr & 0xffffu) == (unsigned)i) ? 0u : 0x8000u);
+    }
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      if (s < nslots) {
+        const unsigned sf = sfs[s];
+        const int e = (int)(sf & 0x3fffu);
+        const int j = T.face_start + e;
+        double *col = S + ((sf >> 15) ? SIDE * FS : 0) + e;
+        if (sf & 0x4000u) {
+          // boundary face: first order (the *_BC.h functors take the cell state as is); the cell centroid is
+          // parked in the unused right half for NoSlip_BC.h:114-139
+#pragma unroll
+          for (int k = 0; k < 5; ++k) col[k * FS] = V[k];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) col[(SIDE + d) * FS] = xc[d];
+        } else {
+          double dx[3];
+          if (SECOND) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) dx[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j) - xc[d];
+          }
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            double v = V[k];
+            if (SECOND) v = fma(lm[k], dx[0] * g[k][0] + dx[1] * g[k][1] + dx[2] * g[k][2], v);  // Flux.h:114-127
+            col[k * FS] = v;
+          }
+          if (VISCOUS) {
+            double av[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) av[d] = __ldg(m.face_geom + (size_t)d * NF + j);
+            col[5 * FS] = txx * av[0] + txy * av[1] + txz * av[2];
+            col[6 * FS] = txy * av[0] + tyy * av[1] + tyz * av[2];
+            col[7 * FS] = txz * av[0] + tyz * av[1] + tzz * av[2];
+            col[8 * FS] = g[4][0] * av[0] + g[4][1] * av[1] + g[4][2] * av[2];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B
+  for (int e = threadIdx.x; e < T.face_count; e += blockDim.x) {
+    const int j = T.face_start + e;
+    const unsigned r16 = __ldg(m.face_lr + j) >> 16;
+    FaceGeom G;
+    load_face_geom(m, NF, j, G);
+    double Vl[5], Vr[5], flux[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) Vl[k] = S[k * FS + e];
+    if (r16 < 0xFFF0u) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) Vr[k] = S[(SIDE + k) * FS + e];
+      face_roe_flux(Vl, Vr, G, flux);
+      if (VISCOUS) {
+        // Viscous_Flux.h:65-98 at the face state 0.5 (Vl' + Vr') (Flux.h:142-143) from the staged halves
+        const double Tf = 0.5 * (Vl[4] + Vr[4]);
+        const double mu = compute_viscosity(Tf);
+        const double kappa_half = 0.5 * compute_thermal_conductivity(mu);
+        const double q0 = S[5 * FS + e] + S[(SIDE + 5) * FS + e];
+        const double q1 = S[6 * FS + e] + S[(SIDE + 6) * FS + e];
+        const double q2 = S[7 * FS + e] + S[(SIDE + 7) * FS + e];
+        const double hh = S[8 * FS + e] + S[(SIDE + 8) * FS + e];
+        const double half_mu = 0.5 * mu;
+        const double uq = (Vl[1] + Vr[1]) * q0 + (Vl[2] + Vr[2]) * q1 + (Vl[3] + Vr[3]) * q2;  // 2 u_face . q
+        flux[1] -= mu * q0;
+        flux[2] -= mu * q1;
+        flux[3] -= mu * q2;
+        flux[4] -= fma(half_mu, uq, kappa_half * hh);
+      }
+    } else {
+      const int type = (int)(0xFFFFu - r16);
+      double area_norm = 0;
+      if (type == 0) {  // Extrapolate_BC.h:82-83
+#pragma unroll
+        for (int k = 0; k < 5; ++k) Vr[k] = Vl[k];
+      } else if (type == 2) {  // Inflow_BC.h:84-90
+        double Ui[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) Ui[k] = m.inflow[k];
+        compute_primitives(Ui, Vr);
+      } else {  // Tangent_BC.h:82-101, NoSlip_BC.h:96-112
+        mirror_state(Vl, G.n, Vr, area_norm);
+      }
+      face_roe_flux(Vl, Vr, G, flux);
+      if (type == 3) {  // NoSlip_BC.h:114-139
+        double xf[3], xc[3], vflux[5];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          xf[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j);
+          xc[d] = S[(SIDE + d) * FS + e];
+        }
+        noslip_viscous_flux(Vl, G.n, area_norm, xf, xc, vflux);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) flux[k] -= vflux[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) S[k * FS + e] = flux[k];
+  }
+  __syncthreads();
+
+  // ---- phase C
+  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
+    const int c = T.cell_start + lc;
+    const double dtv = a.dt * rcp(__ldg(m.cell_vol + c));
+    double R[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const unsigned sf = m.slot_face[(size_t)s * m.slot_stride + c];
+      const int e = (int)(sf & 0x3fffu);
+      const double sg = (sf >> 15) ? dtv : -dtv;  // Flux.h:172-178: left slot holds -flux, right slot +flux
+#pragma unroll
+      for (int k = 0; k < 5; ++k) R[k] = fma(sg, S[k * FS + e], R[k]);
+    }
+    double Wn[5];
+    if (a.kind == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double w = a.Un[(size_t)k * m.stride + c];
+        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, R[k], w);
+        Wn[k] = fma(a.alpha_next, R[k], w);
+      }
+    } else if (a.kind == 1) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, R[k], a.Acc[(size_t)k * m.stride + c]);
+        Wn[k] = fma(a.alpha_next, R[k], a.Un[(size_t)k * m.stride + c]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        Wn[k] = fma(a.beta, R[k], a.Acc[(size_t)k * m.stride + c]);
+        a.Un[(size_t)k * m.stride + c] = Wn[k];
+      }
+    }
+    double Vn[5];
+    compute_primitives(Wn, Vn);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) a.Vnext[(size_t)k * m.stride + c] = Vn[k];
+  }
+}
+#endif  // !MA_STRICT
 
 // U (conservative, owned cells) -> V (primitives): after initial conditions / set_solution
 __global__ void primitives_kernel(const DevMesh m, const double *__restrict__ Un, double *__restrict__ V) {
@@ -436,13 +776,28 @@ __global__ void probe_vanalbada_kernel(int n, const double *dmax, const double *
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------
+#ifdef MA_STRICT
+size_t grad_smem_bytes(const DevMesh &) { return 0; }
+size_t flux_smem_bytes(const DevMesh &m, bool, bool) { return (size_t)5 * m.flux_smem_stride * sizeof(double); }
+#define MA_GRAD_KERNEL grad_limiter_kernel
+#define MA_FLUX_KERNEL flux_rk_kernel
+#else
+size_t grad_smem_bytes(const DevMesh &m) { return (size_t)5 * m.local_smem_stride * sizeof(double); }
+size_t flux_smem_bytes(const DevMesh &m, bool, bool viscous) {
+  return (size_t)(viscous ? 18 : 10) * m.flux_smem_stride * sizeof(double);
+}
+#define MA_GRAD_KERNEL grad_limiter_tile_kernel
+#define MA_FLUX_KERNEL flux_rk_tile_kernel
+#endif
+
 cudaError_t launch_grad_limiter(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                 int tile_begin, int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
+  const size_t smem = grad_smem_bytes(m);
   if (second)
-    grad_limiter_kernel<true><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
+    MA_GRAD_KERNEL<true><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
   else
-    grad_limiter_kernel<false><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
+    MA_GRAD_KERNEL<false><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
   return cudaGetLastError();
 }
 
@@ -451,10 +806,12 @@ cudaError_t flux_rk_prepare(int smem_bytes) {
 #define MA_SET(K)                                                                          \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);    \
   if (e != cudaSuccess) return e;
-  MA_SET((flux_rk_kernel<false, false>))
-  MA_SET((flux_rk_kernel<false, true>))
-  MA_SET((flux_rk_kernel<true, false>))
-  MA_SET((flux_rk_kernel<true, true>))
+  MA_SET((MA_FLUX_KERNEL<false, false>))
+  MA_SET((MA_FLUX_KERNEL<false, true>))
+  MA_SET((MA_FLUX_KERNEL<true, false>))
+  MA_SET((MA_FLUX_KERNEL<true, true>))
+  MA_SET((MA_GRAD_KERNEL<false>))
+  MA_SET((MA_GRAD_KERNEL<true>))
 #undef MA_SET
   return cudaSuccess;
 }
@@ -462,15 +819,15 @@ cudaError_t flux_rk_prepare(int smem_bytes) {
 cudaError_t launch_flux_rk(const DevMesh &m, const StageArgs &a, bool second, bool viscous, int tile_begin,
                            int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
-  const size_t smem = (size_t)5 * m.flux_smem_stride * sizeof(double);
+  const size_t smem = flux_smem_bytes(m, second, viscous);
   if (second && viscous)
-    flux_rk_kernel<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    MA_FLUX_KERNEL<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else if (second)
-    flux_rk_kernel<true, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    MA_FLUX_KERNEL<true, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else if (viscous)
-    flux_rk_kernel<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    MA_FLUX_KERNEL<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else
-    flux_rk_kernel<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    MA_FLUX_KERNEL<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   return cudaGetLastError();
 }
 

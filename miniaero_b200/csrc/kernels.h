@@ -9,6 +9,7 @@ namespace ma {
 
 struct TileInfoDev {
   int cell_start, cell_count, face_start, face_count;
+  int cut_start, halo_start;  // see ma::TileInfo (layout.h)
 };
 
 // Device mesh in the tile-packed structure-of-arrays layout (see DESIGN.md "Data layout in HBM").
@@ -16,13 +17,16 @@ struct DevMesh {
   int n_owned, n_cells, stride;        // cells; SoA component stride
   int n_tiles, slot_stride;
   long n_tile_faces;                   // component stride of face_geom
-  int flux_smem_stride;                // per-component stride of the shared-memory flux staging
+  int flux_smem_stride;                // per-component stride of the shared-memory face staging (>= faces of a tile)
+  int local_smem_stride;               // per-component stride of the shared-memory cell staging (>= cells + cut faces)
   const TileInfoDev *tiles;
   const double *cell_xyz;              // [3][stride]
   const double *cell_vol;              // [stride]
   const uint16_t *slot_face;           // [6][slot_stride]
   const double *face_geom;             // STRICT [12][n_tile_faces]: normal, tangent, binormal, centroid; FAST [6]: normal, centroid
-  const int *face_left, *face_right;   // [n_tile_faces]
+  const int *face_left, *face_right;   // [n_tile_faces] renumbered cell ids (STRICT kernels only)
+  const uint32_t *face_lr;             // [n_tile_faces] tile-local left | right << 16 (boundary: 0xFFFF - type)
+  const int *tile_halo;                // outside cell of every cut face, tile after tile
   double inflow[5];                    // TimeSolverExplicitRK4.h:218-223
 };
 
@@ -48,6 +52,9 @@ struct StageArgs {
   cudaError_t launch_flux_rk(const ma::DevMesh &m, const ma::StageArgs &a, bool second, bool viscous,                \
                              int tile_begin, int ntiles, int threads, cudaStream_t st);                              \
   cudaError_t flux_rk_prepare(int smem_bytes);                                                                       \
+  /* shared memory per CTA of the two stage kernels for this mesh */                                                 \
+  size_t grad_smem_bytes(const ma::DevMesh &m);                                                                      \
+  size_t flux_smem_bytes(const ma::DevMesh &m, bool second, bool viscous);                                                                       \
   /* GasModel.h:70-90 over the owned cells: conservative Un -> primitives V */                                       \
   cudaError_t launch_primitives(const ma::DevMesh &m, const double *Un, double *V, cudaStream_t st);                 \
   /* Initial_Conditions.h:38-133 */                                                                                  \

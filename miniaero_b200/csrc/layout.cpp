@@ -282,23 +282,42 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
     if (on < T.cell_start || on >= T.cell_start + T.cell_count) return true;
     return on < newc;
   };
-  std::vector<long> fstart(n_tiles + 1, 0);
-  int max_faces = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_faces)
+  // is the cell on the other side of (new cell c, slot s) outside the tile?  (cut face)
+  auto is_cut = [&](const TileInfo &T, int newc, int s) -> bool {
+    const int oldc = L.new2old[newc];
+    const int oth = other_cell(cf[(size_t)oldc * 6 + s]);
+    if (oth < 0) return false;
+    if (oth >= n_owned) return true;
+    const int on = L.old2new[oth];
+    return on < T.cell_start || on >= T.cell_start + T.cell_count;
+  };
+  std::vector<long> fstart(n_tiles + 1, 0), hstart(n_tiles + 1, 0);
+  int max_faces = 0, max_local = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_faces, max_local)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
-    int cnt = 0;
+    int cnt = 0, cut = 0;
     for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c)
-      for (int s = 0; s < 6; ++s) cnt += emits(T, c, s) ? 1 : 0;
+      for (int s = 0; s < 6; ++s) {
+        if (!emits(T, c, s)) continue;
+        ++cnt;
+        cut += is_cut(T, c, s) ? 1 : 0;
+      }
     L.tiles[k].face_count = cnt;
+    L.tiles[k].cut_start = cnt - cut;
     max_faces = std::max(max_faces, cnt);
+    max_local = std::max(max_local, T.cell_count + cut);
   }
-  if (max_faces >= 32768) return ma_set_error(MA_ERR_INVALID, "tile has more than 32767 faces; use smaller tile_dims");
+  if (max_faces >= 16384) return ma_set_error(MA_ERR_INVALID, "tile has more than 16383 faces; use smaller tile_dims");
+  if (max_local >= 0xFFF0) return ma_set_error(MA_ERR_INVALID, "tile has too many cells + cut faces; use smaller tile_dims");
   L.max_tile_faces = max_faces;
+  L.max_tile_local = max_local;
   long real = 0;
   for (long k = 0; k < n_tiles; ++k) {
     L.tiles[k].face_start = (int)fstart[k];
+    L.tiles[k].halo_start = (int)hstart[k];
     fstart[k + 1] = fstart[k] + round_up(L.tiles[k].face_count, 16);
+    hstart[k + 1] = hstart[k] + (L.tiles[k].face_count - L.tiles[k].cut_start);
     real += L.tiles[k].face_count;
     if (fstart[k + 1] >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 tile faces");
   }
@@ -308,16 +327,24 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.face_geom.assign((size_t)L.geom_components * NF, 0.0);
   const int GX = with_tangents ? 9 : 3;  // first centroid component
   double frame_err = 0.0;
-  L.face_left.assign(NF, 0);
-  L.face_right.assign(NF, 0);
+  if (with_tangents) {
+    L.face_left.assign(NF, 0);
+    L.face_right.assign(NF, 0);
+  }
+  L.face_lr.assign(NF, 0);
+  L.tile_halo.assign((size_t)hstart[n_tiles], 0);
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
-    int e = 0;
+    int e_closed = 0, e_cut = T.cut_start;
+    // closed / boundary faces first, cut faces last; each group in (cell, slot) order: the face sweep then
+    // walks cells in order and every cell's data is touched within a short window
     for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c) {
       const int oldc = L.new2old[c];
       for (int s = 0; s < 6; ++s) {
         if (!emits(T, c, s)) continue;
+        const bool cut = is_cut(T, c, s);
+        const int e = cut ? e_cut++ : e_closed++;
         const uint32_t ref = cf[(size_t)oldc * 6 + s];
         const int side = (int)(ref & 1);
         const FaceSrc src = face_src(ref);
@@ -345,21 +372,34 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
           err = std::max(err, std::max(std::fabs(nt), std::max(std::fabs(nb), std::fabs(tb))));
           if (!(err <= frame_err)) frame_err = (err == err) ? err : 1e300;
         }
-        L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
+        const int lc = c - T.cell_start;  // tile-local index of the emitting cell
         if (src.bc_type >= 0) {
-          L.face_left[j] = c;
-          L.face_right[j] = bc_code(src.bc_type);
+          L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (1 << 14) | (side << 15));
+          if (with_tangents) {
+            L.face_left[j] = c;
+            L.face_right[j] = bc_code(src.bc_type);
+          }
+          L.face_lr[j] = (uint32_t)lc | ((uint32_t)(0xFFFF - src.bc_type) << 16);
         } else {
+          L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
           const int oth_old = src.f->face_cell_conn[2 * fi + (1 - side)];
           const int oth_new = L.old2new[oth_old];
-          L.face_left[j] = side == 0 ? c : oth_new;
-          L.face_right[j] = side == 0 ? oth_new : c;
-          if (oth_old < n_owned && oth_new >= T.cell_start && oth_new < T.cell_start + T.cell_count) {
+          if (with_tangents) {
+            L.face_left[j] = side == 0 ? c : oth_new;
+            L.face_right[j] = side == 0 ? oth_new : c;
+          }
+          int oth_local;
+          if (cut) {
+            oth_local = T.cell_count + (e - T.cut_start);
+            L.tile_halo[(size_t)T.halo_start + (e - T.cut_start)] = oth_new;
+          } else {
+            oth_local = oth_new - T.cell_start;
             const int os = src.f->cell_flux_index[2 * fi + (1 - side)];
             L.slot_face[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(e | ((1 - side) << 15));
           }
+          L.face_lr[j] = side == 0 ? ((uint32_t)lc | ((uint32_t)oth_local << 16))
+                                   : ((uint32_t)oth_local | ((uint32_t)lc << 16));
         }
-        ++e;
       }
     }
   }

@@ -20,6 +20,9 @@ struct TileInfo {
   int cell_count;
   int face_start;  // first entry of the tile in the tile-packed face arrays
   int face_count;
+  int cut_start;   // tile-local index of the first "cut" face (one cell in the tile, the other — owned by a
+                   // neighbouring tile or a ghost — outside); faces [0, cut_start) are closed or boundary faces
+  int halo_start;  // first entry of the tile in tile_halo; cut face e's outside cell is tile_halo[halo_start + e - cut_start]
 };
 
 struct HostLayout {
@@ -38,7 +41,7 @@ struct HostLayout {
   // cell SoA (renumbered): xyz[3][stride], vol[stride]
   std::vector<double> cell_xyz, cell_vol;
   // slot map: slot_face[s][cell] (owned cells only, stride = n_owned rounded up to 32):
-  // bits 0..14 tile-local face index, bit 15 = 1 when the cell is elem2 (right) of the face
+  // bits 0..13 tile-local face index, bit 14 = 1 for a boundary face, bit 15 = 1 when the cell is elem2 (right)
   std::vector<uint16_t> slot_face;
   int slot_stride = 0;
 
@@ -49,6 +52,11 @@ struct HostLayout {
   double max_frame_error = 0.0;  // worst deviation of (n^, t, b/|a|) from an orthonormal frame over all faces
   std::vector<double> face_geom;
   std::vector<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
+  // tile-local connectivity: low 16 bits = left cell, high 16 bits = right cell, as indices into the tile's
+  // [own cells | outside cells of its cut faces] list; a boundary face has right = 0xFFFF - ma_bc_type
+  std::vector<uint32_t> face_lr;
+  std::vector<int> tile_halo;  // renumbered id of the outside cell of every cut face, tile after tile
+  int max_tile_local = 0;      // largest (cells + cut faces) of a tile
 
   // halo lists in renumbered ids, grouped by neighbour rank ascending
   std::vector<int> send_ids, recv_ids;

@@ -99,6 +99,8 @@ struct ma_solver {
   double *d_xyz = nullptr, *d_vol = nullptr, *d_geom = nullptr;
   uint16_t *d_slot = nullptr;
   int *d_fl = nullptr, *d_fr = nullptr, *d_old2new = nullptr, *d_send_ids = nullptr, *d_recv_ids = nullptr;
+  uint32_t *d_face_lr = nullptr;
+  int *d_tile_halo = nullptr;
   double *d_Un = nullptr, *d_Acc = nullptr, *d_V[2] = {nullptr, nullptr}, *d_grad = nullptr, *d_lim = nullptr;
   int vcur = 0;  // d_V[vcur] holds the primitives of the state the next stage is evaluated at
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr, *d_stage = nullptr;
@@ -355,7 +357,7 @@ void ma_solver_destroy(ma_solver *S) {
   if (S->st) cudaStreamSynchronize(S->st);
   if (S->cs) cudaStreamSynchronize(S->cs);
   void *ptrs[] = {S->d_tiles, S->d_xyz,  S->d_vol,  S->d_geom, S->d_slot,    S->d_fl,      S->d_fr,   S->d_old2new,
-                  S->d_send_ids, S->d_recv_ids, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
+                  S->d_send_ids, S->d_recv_ids, S->d_face_lr, S->d_tile_halo, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
                   S->d_sendbuf, S->d_recvbuf, S->d_stage};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -387,9 +389,12 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   int rc = check_device(cfg.device);
   if (rc) return rc;
 
-  // tile size: 8x8x8 unless told otherwise
+  // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 8x4x4 for the FAST tile kernels, whose
+  // shared-memory face staging (18 doubles per tile face) should leave room for three CTAs per SM
+  const int td_default[2][3] = {{8, 4, 4}, {8, 8, 8}};
   int td[3];
-  for (int d = 0; d < 3; ++d) td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : 8;
+  for (int d = 0; d < 3; ++d)
+    td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : td_default[cfg.arith == MA_ARITH_STRICT ? 1 : 0][d];
   ma::HostLayout L;
   rc = ma::build_layout(*mesh, td, cfg.arith == MA_ARITH_STRICT, L);
   if (rc) return rc;
@@ -414,7 +419,7 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   S->n_tile_faces_real = L.n_tile_faces_real;
   S->peer_rank = L.peer_rank, S->peer_send = L.peer_send_count, S->peer_recv = L.peer_recv_count;
   S->n_send = (int)L.send_ids.size(), S->n_recv = (int)L.recv_ids.size();
-  if (cfg.block_threads > 0) S->flux_threads = std::min(256, (cfg.block_threads + 31) / 32 * 32);
+  if (cfg.block_threads > 0) S->flux_threads = S->grad_threads = std::min(256, (cfg.block_threads + 31) / 32 * 32);
 
 #define MA_TRY(expr)        \
   do {                      \
@@ -454,7 +459,8 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   {
     std::vector<ma::TileInfoDev> tiles(L.tiles.size());
     for (size_t i = 0; i < tiles.size(); ++i)
-      tiles[i] = {L.tiles[i].cell_start, L.tiles[i].cell_count, L.tiles[i].face_start, L.tiles[i].face_count};
+      tiles[i] = {L.tiles[i].cell_start, L.tiles[i].cell_count, L.tiles[i].face_start, L.tiles[i].face_count,
+                  L.tiles[i].cut_start, L.tiles[i].halo_start};
     MA_TRY(dev_upload(&S->d_tiles, tiles, &S->device_bytes));
   }
   MA_TRY(dev_upload(&S->d_xyz, L.cell_xyz, &S->device_bytes));
@@ -464,6 +470,8 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_fr, L.face_right, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_face_lr, L.face_lr, &S->device_bytes));
+  MA_TRY(dev_upload(&S->d_tile_halo, L.tile_halo, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_old2new, L.old2new, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_send_ids, L.send_ids, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_recv_ids, L.recv_ids, &S->device_bytes));
@@ -494,6 +502,9 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   m.slot_stride = L.slot_stride;
   m.n_tile_faces = L.n_tile_faces;
   m.flux_smem_stride = (L.max_tile_faces + 15) / 16 * 16 + 1;  // odd stride: conflict-free across components
+  m.local_smem_stride = (L.max_tile_local + 15) / 16 * 16 + 1;
+  m.face_lr = S->d_face_lr;
+  m.tile_halo = S->d_tile_halo;
   m.tiles = S->d_tiles;
   m.cell_xyz = S->d_xyz;
   m.cell_vol = S->d_vol;
@@ -503,12 +514,23 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   m.face_right = S->d_fr;
   // inflow state, TimeSolverExplicitRK4.h:218-223
   m.inflow[0] = 0.5805, m.inflow[1] = 503.96, m.inflow[2] = 0.0, m.inflow[3] = 0.0, m.inflow[4] = 343750.0;
-  const int smem = 5 * m.flux_smem_stride * (int)sizeof(double);
-  if (smem > 227 * 1024) {
-    ma_solver_destroy(S);
-    return ma_set_error(MA_ERR_INVALID, "tile needs more than 227 KB of shared memory; use smaller tile_dims");
+  {
+    const bool strict = S->strict;
+    const size_t fsm = strict ? ma_strict::flux_smem_bytes(m, S->second, S->viscous) : ma_fast::flux_smem_bytes(m, S->second, S->viscous);
+    const size_t gsm = strict ? ma_strict::grad_smem_bytes(m) : ma_fast::grad_smem_bytes(m);
+    const size_t smem = std::max(fsm, gsm);
+    if (smem > 227 * 1024) {
+      ma_solver_destroy(S);
+      return ma_set_error(MA_ERR_INVALID, "tile needs more than 227 KB of shared memory; use smaller tile_dims");
+    }
+    MA_CU(api_of(strict).prepare((int)smem));
+    if (cfg.block_threads <= 0 && !strict) {
+      // FAST tile kernels: one thread per tile cell, at least 128 (phase B walks ~3.5 faces per cell)
+      int t = std::max(128, (L.max_tile_cells + 31) / 32 * 32);
+      S->flux_threads = std::min(256, t);
+      S->grad_threads = std::min(256, t);
+    }
   }
-  MA_CU(api_of(S->strict).prepare(smem));
   S->tm.device_bytes = S->device_bytes;
   S->tm.num_tiles = S->n_tiles;
   S->tm.tile_faces_total = (int)std::min<long>(L.n_tile_faces_real, 2147483647L);

@@ -11,10 +11,18 @@ def run(nx,ny,nz,second,visc,ptype=0,steps=5,tile=(0,0,0),bt=0,lx=0.3048,ly=1.0,
     print(json.dumps(dict(n=(nx,ny,nz),second=second,visc=visc,tile=tile,bt=bt,mesh_s=round(tm,2),layout_s=round(tl,2),ms_per_step=round(1e3*T['step_seconds']/steps,3),cell_updates_per_s='%.3e'%cu,
         frac_roofline=round(cu*(4648 if second else 1928)/6549.4e9,4),grad_ms=round(1e3*P['grad_seconds']/2,3),flux_ms=round(1e3*P['flux_seconds']/2,3),dev_GB=round(T['device_bytes']/1e9,2),tiles=T['num_tiles'])),flush=True)
 if __name__=='__main__':
-    run(128,128,128,1,1)
-    run(128,128,128,0,0)
-    run(256,256,128,1,1)
-    run(256,256,128,1,1,tile=(8,8,4),bt=128)
-    run(256,256,128,1,1,tile=(4,4,8),bt=128)
-    run(256,256,128,1,1,bt=128)
-    run(256,256,128,1,0)
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == 'tiles':
+        for tile, bt in [((0,0,0),0), ((8,4,4),256), ((4,4,8),128), ((8,8,4),256), ((8,8,4),128), ((16,4,4),256), ((8,8,8),256), ((4,4,4),128), ((4,4,4),64)]:
+            try:
+                run(256,256,128,1,1,tile=tile,bt=bt)
+            except Exception as e:
+                print('FAILED', tile, bt, e, flush=True)
+        run(256,256,128,1,0)
+        run(256,256,128,0,0)
+        run(256,128,64,1,1,ptype=1,lx=2.0,ly=0.008,lz=1.0,dt=3e-8)
+    else:
+        run(128,128,128,1,1)
+        run(128,128,128,0,0)
+        run(256,256,128,1,1)
+        run(256,256,128,1,0)
