@@ -19,11 +19,11 @@
 // launch bounds (max threads per CTA, min resident CTAs per SM) of the two stage kernels
 #ifndef MA_GRAD_THREADS
 #define MA_GRAD_THREADS 256
-#define MA_GRAD_MINB 1
+#define MA_GRAD_MINB 2
 #endif
 #ifndef MA_FLUX_THREADS
 #define MA_FLUX_THREADS 256
-#define MA_FLUX_MINB 1
+#define MA_FLUX_MINB 2
 #endif
 
 namespace MA_NS {
@@ -31,6 +31,14 @@ namespace MA_NS {
 using ma::DevMesh;
 using ma::StageArgs;
 using ma::TileInfoDev;
+
+// 8-byte asynchronous global -> shared copy (LDGSTS): the data lands in shared memory without occupying a
+// register or a scoreboard slot of the issuing thread
+MA_DEV void cp_async8(double *smem_dst, const double *gmem_src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+MA_DEV void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 MA_DEV void load_state(const double *__restrict__ base, int stride, int c, double (&v)[5]) {
 #pragma unroll
@@ -87,8 +95,12 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       g[k][0] = g[k][1] = g[k][2] = 0;
+#ifdef MA_STRICT
       mn[k] = 1.0e300;   // StencilLimiter.h:227-228
       mx[k] = -1.0e300;
+#else
+      mn[k] = mx[k] = V[k];  // every face contributes min/max(V, Vn): start from V, fold the neighbours in
+#endif
     }
     int fj[6];
 #pragma unroll
@@ -129,8 +141,13 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
         if (SECOND) {
 #pragma unroll
           for (int k = 0; k < 5; ++k) {
+#ifdef MA_STRICT
             mn[k] = fmin(mn[k], fmin(Vn[k], V[k]));  // StencilLimiter.h:139-140,272-273
             mx[k] = fmax(mx[k], fmax(Vn[k], V[k]));
+#else
+            mn[k] = fmin(mn[k], Vn[k]);
+            mx[k] = fmax(mx[k], Vn[k]);
+#endif
           }
         }
       } else {
@@ -144,10 +161,12 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
 #pragma unroll
           for (int d = 0; d < 3; ++d) g[k][d] = fma(two_v, n[d], g[k][d]);
 #endif
+#ifdef MA_STRICT
           if (SECOND) {
             mn[k] = fmin(mn[k], V[k]);
             mx[k] = fmax(mx[k], V[k]);
           }
+#endif
         }
       }
     }
@@ -173,11 +192,11 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
       double phi[5] = {1.0, 1.0, 1.0, 1.0, 1.0};  // StencilLimiter.h:308-311
 #else
       double pN[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pD[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
-      double dumax[5], dumin[5];
+      double dumax[5], ndumin[5];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         dumax[k] = mx[k] - V[k];
-        dumin[k] = mn[k] - V[k];
+        ndumin[k] = V[k] - mn[k];
       }
 #endif
 #pragma unroll
@@ -200,9 +219,13 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
           const double dumin = mn[k] - V[k];
           phi[k] = fmin(phi[k], venkat_limit(dumax, dumin, dU, dist));  // StencilLimiter.h:451-455, 345-346
 #else
-          double N, D;
-          venkat_fraction(dumax[k], dumin[k], dU, dist, N, D);
-          venkat_fraction_min(N, D, pN[k], pD[k]);
+          // VenkatLimiter.h:45-73 with a = |du|, mm = |dumax| or |dumin| by the sign of du and the common
+          // factor du cancelled: phi = (mm^2 + eps2 + 2 a mm) / (mm^2 + eps2 + a (2a + mm)); phi -> 1 as a -> 0
+          const double aa = fabs(dU);
+          const double mm = dU > 0.0 ? dumax[k] : ndumin[k];
+          const double base = fma(mm, mm, dist);
+          const double a2 = aa + aa;
+          venkat_fraction_min(fma(a2, mm, base), fma(aa, a2 + mm, base), pN[k], pD[k]);
 #endif
         }
       }
@@ -225,7 +248,23 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   const size_t NF = (size_t)m.n_tile_faces;
   const int FS = m.flux_smem_stride;
+  const int CS = m.rk_smem_stride;
   const double *__restrict__ V_ = a.V;
+  double *srk = sflux + 5 * FS;  // [11][CS]: volume, Un[5], Acc[5] of the tile's cells for phase 2
+
+  // ---- phase 0: start the asynchronous copy of the phase-2 operands; it completes behind phase 1
+  for (int lc = threadIdx.x; lc < T.cell_count; lc += blockDim.x) {
+    const int c = T.cell_start + lc;
+    cp_async8(srk + lc, m.cell_vol + c);
+    if (a.kind != 2) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cp_async8(srk + (1 + k) * CS + lc, a.Un + (size_t)k * m.stride + c);
+    }
+    if (a.kind != 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cp_async8(srk + (6 + k) * CS + lc, a.Acc + (size_t)k * m.stride + c);
+    }
+  }
 
   // ---- phase 1: one flux per tile face
   for (int e = threadIdx.x; e < T.face_count; e += blockDim.x) {
@@ -258,7 +297,11 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
             const double gr = __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + r);
             tl += dl[d] * gl;  // Flux.h:114-121
             tr += dr[d] * gr;
+#ifdef MA_STRICT
             if (VISCOUS) gf[k][d] = 0.5 * (gl + gr);  // Flux.h:146-149
+#else
+            if (VISCOUS) gf[k][d] = gl + gr;  // twice the face gradient; the 0.5 is folded into the viscosity
+#endif
           }
           Vl[k] += tl * __ldg(a.lim + (size_t)k * m.stride + l);  // Flux.h:124-127
           Vr[k] += tr * __ldg(a.lim + (size_t)k * m.stride + r);
@@ -267,18 +310,42 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
 #pragma unroll
         for (int k = 0; k < 5; ++k)
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-            gf[k][d] = 0.5 * (__ldg(a.grad + (size_t)(k * 3 + d) * m.stride + l) +
-                              __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + r));
+          for (int d = 0; d < 3; ++d) {
+            const double gsum = __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + l) +
+                                __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + r);
+#ifdef MA_STRICT
+            gf[k][d] = 0.5 * gsum;
+#else
+            gf[k][d] = gsum;
+#endif
+          }
       }
       face_roe_flux(Vl, Vr, G, flux);
       if (VISCOUS) {
+#ifdef MA_STRICT
         double Vf[5], vflux[5];
 #pragma unroll
         for (int k = 0; k < 5; ++k) Vf[k] = 0.5 * (Vl[k] + Vr[k]);  // Flux.h:142-143
         viscous_flux(gf, Vf, G.n, vflux);
 #pragma unroll
         for (int k = 0; k < 5; ++k) flux[k] -= vflux[k];
+#else
+        // Viscous_Flux.h:65-98 with gf = 2 x face gradient: q_i = sum_j tau_ij(gf) a_j, hh = gf_T . a
+        const double third_div = (gf[1][0] + gf[2][1] + gf[3][2]) * (1.0 / 3.0);
+        const double txx = gf[1][0] - third_div, tyy = gf[2][1] - third_div, tzz = gf[3][2] - third_div;
+        const double txy = 0.5 * (gf[1][1] + gf[2][0]), txz = 0.5 * (gf[1][2] + gf[3][0]);
+        const double tyz = 0.5 * (gf[2][2] + gf[3][1]);
+        const double q0 = txx * G.n[0] + txy * G.n[1] + txz * G.n[2];
+        const double q1 = txy * G.n[0] + tyy * G.n[1] + tyz * G.n[2];
+        const double q2 = txz * G.n[0] + tyz * G.n[1] + tzz * G.n[2];
+        const double hh = gf[4][0] * G.n[0] + gf[4][1] * G.n[1] + gf[4][2] * G.n[2];
+        const double mu = compute_viscosity(0.5 * (Vl[4] + Vr[4]));
+        const double uq = (Vl[1] + Vr[1]) * q0 + (Vl[2] + Vr[2]) * q1 + (Vl[3] + Vr[3]) * q2;
+        flux[1] -= mu * q0;
+        flux[2] -= mu * q1;
+        flux[3] -= mu * q2;
+        flux[4] -= fma(0.5 * mu, uq, 0.5 * compute_thermal_conductivity(mu) * hh);
+#endif
       }
     } else {
       // boundary face, always first order (Extrapolate_BC.h, Tangent_BC.h, Inflow_BC.h, NoSlip_BC.h)
@@ -312,15 +379,16 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
 #pragma unroll
     for (int k = 0; k < 5; ++k) sflux[k * FS + e] = flux[k];
   }
+  cp_async_commit_wait_all();
   __syncthreads();
 
   // ---- phase 2: slot-ordered gather, residual, RK update; the next stage state is stored as primitives
   for (int lc = threadIdx.x; lc < T.cell_count; lc += blockDim.x) {
     const int c = T.cell_start + lc;
 #ifdef MA_STRICT
-    const double dtv = a.dt / __ldg(m.cell_vol + c);  // Flux.h:224-225: dt_/volume_(i) * flux
+    const double dtv = a.dt / srk[lc];  // Flux.h:224-225: dt_/volume_(i) * flux
 #else
-    const double dtv = a.dt * rcp(__ldg(m.cell_vol + c));
+    const double dtv = a.dt * rcp(srk[lc]);
 #endif
     double R[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -338,20 +406,20 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
     if (a.kind == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double w = a.Un[(size_t)k * m.stride + c];
+        const double w = srk[(1 + k) * CS + lc];
         a.Acc[(size_t)k * m.stride + c] = w + a.beta * R[k];
         Wn[k] = w + a.alpha_next * R[k];
       }
     } else if (a.kind == 1) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        a.Acc[(size_t)k * m.stride + c] = a.Acc[(size_t)k * m.stride + c] + a.beta * R[k];
-        Wn[k] = a.Un[(size_t)k * m.stride + c] + a.alpha_next * R[k];
+        a.Acc[(size_t)k * m.stride + c] = srk[(6 + k) * CS + lc] + a.beta * R[k];
+        Wn[k] = srk[(1 + k) * CS + lc] + a.alpha_next * R[k];
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        Wn[k] = a.Acc[(size_t)k * m.stride + c] + a.beta * R[k];
+        Wn[k] = srk[(6 + k) * CS + lc] + a.beta * R[k];
         a.Un[(size_t)k * m.stride + c] = Wn[k];
       }
     }
@@ -361,7 +429,6 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
     for (int k = 0; k < 5; ++k) a.Vnext[(size_t)k * m.stride + c] = Vn[k];
   }
 }
-
 
 #ifndef MA_STRICT
 // ======================================================================================================
@@ -776,28 +843,39 @@ __global__ void probe_vanalbada_kernel(int n, const double *dmax, const double *
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------
+static size_t gather_flux_smem(const DevMesh &m) {
+  return ((size_t)5 * m.flux_smem_stride + (size_t)11 * m.rk_smem_stride) * sizeof(double);
+}
 #ifdef MA_STRICT
 size_t grad_smem_bytes(const DevMesh &) { return 0; }
-size_t flux_smem_bytes(const DevMesh &m, bool, bool) { return (size_t)5 * m.flux_smem_stride * sizeof(double); }
-#define MA_GRAD_KERNEL grad_limiter_kernel
-#define MA_FLUX_KERNEL flux_rk_kernel
+size_t flux_smem_bytes(const DevMesh &m, bool, bool) { return gather_flux_smem(m); }
 #else
-size_t grad_smem_bytes(const DevMesh &m) { return (size_t)5 * m.local_smem_stride * sizeof(double); }
+size_t grad_smem_bytes(const DevMesh &m) {
+  return m.grad_variant == 1 ? (size_t)5 * m.local_smem_stride * sizeof(double) : 0;
+}
 size_t flux_smem_bytes(const DevMesh &m, bool, bool viscous) {
+  if (m.flux_variant != 1) return gather_flux_smem(m);
   return (size_t)(viscous ? 18 : 10) * m.flux_smem_stride * sizeof(double);
 }
-#define MA_GRAD_KERNEL grad_limiter_tile_kernel
-#define MA_FLUX_KERNEL flux_rk_tile_kernel
 #endif
 
 cudaError_t launch_grad_limiter(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                 int tile_begin, int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
   const size_t smem = grad_smem_bytes(m);
+#ifndef MA_STRICT
+  if (m.grad_variant == 1) {
+    if (second)
+      grad_limiter_tile_kernel<true><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
+    else
+      grad_limiter_tile_kernel<false><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
+    return cudaGetLastError();
+  }
+#endif
   if (second)
-    MA_GRAD_KERNEL<true><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
+    grad_limiter_kernel<true><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
   else
-    MA_GRAD_KERNEL<false><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
+    grad_limiter_kernel<false><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
   return cudaGetLastError();
 }
 
@@ -806,12 +884,18 @@ cudaError_t flux_rk_prepare(int smem_bytes) {
 #define MA_SET(K)                                                                          \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);    \
   if (e != cudaSuccess) return e;
-  MA_SET((MA_FLUX_KERNEL<false, false>))
-  MA_SET((MA_FLUX_KERNEL<false, true>))
-  MA_SET((MA_FLUX_KERNEL<true, false>))
-  MA_SET((MA_FLUX_KERNEL<true, true>))
-  MA_SET((MA_GRAD_KERNEL<false>))
-  MA_SET((MA_GRAD_KERNEL<true>))
+  MA_SET((flux_rk_kernel<false, false>))
+  MA_SET((flux_rk_kernel<false, true>))
+  MA_SET((flux_rk_kernel<true, false>))
+  MA_SET((flux_rk_kernel<true, true>))
+#ifndef MA_STRICT
+  MA_SET((flux_rk_tile_kernel<false, false>))
+  MA_SET((flux_rk_tile_kernel<false, true>))
+  MA_SET((flux_rk_tile_kernel<true, false>))
+  MA_SET((flux_rk_tile_kernel<true, true>))
+  MA_SET((grad_limiter_tile_kernel<false>))
+  MA_SET((grad_limiter_tile_kernel<true>))
+#endif
 #undef MA_SET
   return cudaSuccess;
 }
@@ -820,14 +904,27 @@ cudaError_t launch_flux_rk(const DevMesh &m, const StageArgs &a, bool second, bo
                            int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
   const size_t smem = flux_smem_bytes(m, second, viscous);
+#ifndef MA_STRICT
+  if (m.flux_variant == 1) {
+    if (second && viscous)
+      flux_rk_tile_kernel<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    else if (second)
+      flux_rk_tile_kernel<true, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    else if (viscous)
+      flux_rk_tile_kernel<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    else
+      flux_rk_tile_kernel<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    return cudaGetLastError();
+  }
+#endif
   if (second && viscous)
-    MA_FLUX_KERNEL<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    flux_rk_kernel<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else if (second)
-    MA_FLUX_KERNEL<true, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    flux_rk_kernel<true, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else if (viscous)
-    MA_FLUX_KERNEL<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    flux_rk_kernel<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else
-    MA_FLUX_KERNEL<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
+    flux_rk_kernel<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,8 @@ struct DevMesh {
   int n_tiles, slot_stride;
   long n_tile_faces;                   // component stride of face_geom
   int flux_smem_stride;                // per-component stride of the shared-memory face staging (>= faces of a tile)
+  int rk_smem_stride;                  // per-component stride of the staged RK operands (>= cells of a tile)
+  int grad_variant, flux_variant;      // FAST kernels: 0 = gather kernels, 1 = shared-memory tile kernels
   int local_smem_stride;               // per-component stride of the shared-memory cell staging (>= cells + cut faces)
   const TileInfoDev *tiles;
   const double *cell_xyz;              // [3][stride]

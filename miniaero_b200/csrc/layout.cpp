@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #ifdef _OPENMP
@@ -24,6 +25,19 @@ struct FaceSrc {  // where global face g lives in the caller's arrays
 };
 
 inline int round_up(long v, int m) { return (int)(((v + m - 1) / m) * m); }
+
+// 3 x 21-bit Morton (Z-order) key: consecutive tiles are spatial neighbours in all three directions, so the
+// cells a tile reads across its cut faces were touched by a recently scheduled CTA and are still in L2
+inline uint64_t spread3(uint64_t v) {
+  v &= 0x1fffffULL;
+  v = (v | v << 32) & 0x1f00000000ffffULL;
+  v = (v | v << 16) & 0x1f0000ff0000ffULL;
+  v = (v | v << 8) & 0x100f00f00f00f00fULL;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+  v = (v | v << 2) & 0x1249249249249249ULL;
+  return v;
+}
+inline uint64_t morton3(long x, long y, long z) { return spread3((uint64_t)x) << 2 | spread3((uint64_t)y) << 1 | spread3((uint64_t)z); }
 
 }  // namespace
 
@@ -167,6 +181,8 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   long ntile_d[3];
   for (int d = 0; d < 3; ++d) ntile_d[d] = (nbin[d] + L.tile_dims[d] - 1) / L.tile_dims[d];
 
+  const char *order_env = getenv("MINIAERO_TILE_ORDER");  // experiment knob: "linear" = x-major tile order
+  const bool linear_order = order_env && !strcmp(order_env, "linear");
   struct Key {
     uint64_t tile;
     uint32_t local;
@@ -182,7 +198,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
       t[d] = q[d] / L.tile_dims[d];
       l[d] = q[d] % L.tile_dims[d];
     }
-    keys[c].tile = ((uint64_t)t[0] * ntile_d[1] + t[1]) * ntile_d[2] + t[2];
+    keys[c].tile = linear_order ? ((uint64_t)t[0] * ntile_d[1] + t[1]) * ntile_d[2] + t[2] : morton3(t[0], t[1], t[2]);
     keys[c].local = (uint32_t)((l[0] * L.tile_dims[1] + l[1]) * L.tile_dims[2] + l[2]);
     keys[c].cell = (int)c;
   }
@@ -327,10 +343,8 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.face_geom.assign((size_t)L.geom_components * NF, 0.0);
   const int GX = with_tangents ? 9 : 3;  // first centroid component
   double frame_err = 0.0;
-  if (with_tangents) {
-    L.face_left.assign(NF, 0);
-    L.face_right.assign(NF, 0);
-  }
+  L.face_left.assign(NF, 0);
+  L.face_right.assign(NF, 0);
   L.face_lr.assign(NF, 0);
   L.tile_halo.assign((size_t)hstart[n_tiles], 0);
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
@@ -375,19 +389,15 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
         const int lc = c - T.cell_start;  // tile-local index of the emitting cell
         if (src.bc_type >= 0) {
           L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (1 << 14) | (side << 15));
-          if (with_tangents) {
-            L.face_left[j] = c;
-            L.face_right[j] = bc_code(src.bc_type);
-          }
+          L.face_left[j] = c;
+          L.face_right[j] = bc_code(src.bc_type);
           L.face_lr[j] = (uint32_t)lc | ((uint32_t)(0xFFFF - src.bc_type) << 16);
         } else {
           L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
           const int oth_old = src.f->face_cell_conn[2 * fi + (1 - side)];
           const int oth_new = L.old2new[oth_old];
-          if (with_tangents) {
-            L.face_left[j] = side == 0 ? c : oth_new;
-            L.face_right[j] = side == 0 ? oth_new : c;
-          }
+          L.face_left[j] = side == 0 ? c : oth_new;
+          L.face_right[j] = side == 0 ? oth_new : c;
           int oth_local;
           if (cut) {
             oth_local = T.cell_count + (e - T.cut_start);

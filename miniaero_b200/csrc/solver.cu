@@ -391,7 +391,7 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
 
   // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 8x4x4 for the FAST tile kernels, whose
   // shared-memory face staging (18 doubles per tile face) should leave room for three CTAs per SM
-  const int td_default[2][3] = {{8, 4, 4}, {8, 8, 8}};
+  const int td_default[2][3] = {{8, 8, 4}, {8, 8, 8}};
   int td[3];
   for (int d = 0; d < 3; ++d)
     td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : td_default[cfg.arith == MA_ARITH_STRICT ? 1 : 0][d];
@@ -503,6 +503,12 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   m.n_tile_faces = L.n_tile_faces;
   m.flux_smem_stride = (L.max_tile_faces + 15) / 16 * 16 + 1;  // odd stride: conflict-free across components
   m.local_smem_stride = (L.max_tile_local + 15) / 16 * 16 + 1;
+  m.rk_smem_stride = (L.max_tile_cells + 15) / 16 * 16 + 1;
+  {  // experiment knobs (FAST only): MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tile
+    const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
+    m.grad_variant = (gv && !strcmp(gv, "gather")) ? 0 : 1;  // default: shared-memory staged neighbours
+    m.flux_variant = (fv && !strcmp(fv, "tile")) ? 1 : 0;
+  }
   m.face_lr = S->d_face_lr;
   m.tile_halo = S->d_tile_halo;
   m.tiles = S->d_tiles;
@@ -525,10 +531,8 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
     }
     MA_CU(api_of(strict).prepare((int)smem));
     if (cfg.block_threads <= 0 && !strict) {
-      // FAST tile kernels: one thread per tile cell, at least 128 (phase B walks ~3.5 faces per cell)
-      int t = std::max(128, (L.max_tile_cells + 31) / 32 * 32);
-      S->flux_threads = std::min(256, t);
-      S->grad_threads = std::min(256, t);
+      S->flux_threads = 256;
+      S->grad_threads = 128;
     }
   }
   S->tm.device_bytes = S->device_bytes;

@@ -12,7 +12,18 @@ def run(nx,ny,nz,second,visc,ptype=0,steps=5,tile=(0,0,0),bt=0,lx=0.3048,ly=1.0,
         frac_roofline=round(cu*(4648 if second else 1928)/6549.4e9,4),grad_ms=round(1e3*P['grad_seconds']/2,3),flux_ms=round(1e3*P['flux_seconds']/2,3),dev_GB=round(T['device_bytes']/1e9,2),tiles=T['num_tiles'])),flush=True)
 if __name__=='__main__':
     import sys
-    if len(sys.argv) > 1 and sys.argv[1] == 'tiles':
+    if len(sys.argv) > 1 and sys.argv[1] == 'variants':
+        import os
+        for gv, fv, tile, bt in [('gather','gather',(8,8,4),0), ('gather','gather',(8,8,8),0), ('gather','gather',(8,4,4),0), ('gather','gather',(8,8,4),128),
+                                 ('tile','gather',(8,8,4),0), ('tile','gather',(8,4,4),0), ('tile','gather',(8,8,8),0),
+                                 ('gather','tile',(8,4,4),128), ('tile','tile',(8,4,4),128)]:
+            os.environ['MINIAERO_GRAD_KERNEL'] = gv; os.environ['MINIAERO_FLUX_KERNEL'] = fv
+            print(gv, fv, end=' ')
+            try:
+                run(256,256,128,1,1,tile=tile,bt=bt)
+            except Exception as e:
+                print('FAILED', tile, bt, e, flush=True)
+    elif len(sys.argv) > 1 and sys.argv[1] == 'tiles':
         for tile, bt in [((0,0,0),0), ((8,4,4),256), ((4,4,8),128), ((8,8,4),256), ((8,8,4),128), ((16,4,4),256), ((8,8,8),256), ((4,4,4),128), ((4,4,4),64)]:
             try:
                 run(256,256,128,1,1,tile=tile,bt=bt)
