@@ -9,6 +9,7 @@
 #   miniAero.cell.omp    -DCELL_FLUX      -fopenmp  : CPU baseline ("reference source on an OpenMP loop")
 #   miniAero.atomics     -DATOMICS_FLUX   serial    : the reference Makefile's default build (noise floor)
 #   miniAero.atomics.omp -DATOMICS_FLUX   -fopenmp
+#   miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 over oracle/mpi_standin (N cooperating processes)
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${MINIAERO_REFERENCE:-/root/reference/kokkos}"
@@ -23,7 +24,7 @@ SRCS="Main.C Parallel3DMesh.C MeshProcessor.C Face.C Cell.C ElementTopo.C Elemen
 COMMON="-O3 -std=gnu++17 -w -ffp-contract=off -I$HERE/kokkos_standin -I$REF"
 build() { # name, flags
   local name="$1"; shift
-  if [ "$OUT/$name" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] && [ "$OUT/$name" -nt "$HERE/build_ref.sh" ]; then return; fi
+  if [ "$OUT/$name" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] && [ "$OUT/$name" -nt "$HERE/build_ref.sh" ] && [ "$OUT/$name" -nt "$HERE/mpi_standin/mpi.h" ]; then return; fi
   (cd "$REF" && g++ $COMMON "$@" $SRCS -o "$OUT/$name")
   echo "built $OUT/$name"
 }
@@ -31,3 +32,6 @@ build miniAero.cell        -DCELL_FLUX
 build miniAero.cell.omp    -DCELL_FLUX -fopenmp
 build miniAero.atomics     -DATOMICS_FLUX
 build miniAero.atomics.omp -DATOMICS_FLUX -fopenmp
+# the reference's WITH_MPI path (block decomposition + ghost exchange) over the file-based MPI stand-in:
+# full-precision per-rank results for the multi-GPU parity tests
+build miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 -I$HERE/mpi_standin

@@ -89,8 +89,11 @@ inline void dump(const std::string &label, const void *p, size_t bytes, size_t e
                  int rank) {
   const char *dir = std::getenv("MINIAERO_DUMP_DIR");
   if (!dir || !p) return;
+  // optional filter: only views whose label appears in the comma-separated $MINIAERO_DUMP_LABELS
+  const char *only = std::getenv("MINIAERO_DUMP_LABELS");
+  if (only && *only && (std::string(",") + only + ",").find("," + label + ",") == std::string::npos) return;
   char name[1024];
-  std::snprintf(name, sizeof(name), "%s/%04d_%s.bin", dir, dump_seq()++, label.c_str());
+  std::snprintf(name, sizeof(name), "%s/%06d_%s.bin", dir, dump_seq()++, label.c_str());
   FILE *f = std::fopen(name, "wb");
   if (!f) return;
   // header: magic, element size, rank, dims[4] (all int64), then raw data

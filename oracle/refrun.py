@@ -74,8 +74,47 @@ def run_reference(inp, kind="cell", omp=False, threads=None, dump=True, workdir=
     dumps = []
     if dump:
         for name in sorted(os.listdir(env["MINIAERO_DUMP_DIR"])):
-            dumps.append((name[5:-4], read_dump(os.path.join(env["MINIAERO_DUMP_DIR"], name))))
+            dumps.append((name.split("_", 1)[1][:-4], read_dump(os.path.join(env["MINIAERO_DUMP_DIR"], name))))
     out["dumps"] = dumps
+    return out
+
+
+def run_reference_parallel(inp, nranks, dump=True, timeout=3600, labels="solution_n"):
+    """Run the reference's WITH_MPI build (oracle/_ref/miniAero.cell.mpi, MPI = oracle/mpi_standin) as `nranks`
+    cooperating processes.  Returns a list, per rank, of dict(results, dumps, stdout)."""
+    exe = os.path.join(REF_DIR, "miniAero.cell.mpi")
+    if not (os.path.isfile(exe) and os.access(exe, os.X_OK)):
+        raise FileNotFoundError("oracle/_ref/miniAero.cell.mpi not built (run oracle/build_ref.sh)")
+    tmp = tempfile.mkdtemp(prefix="miniaero_refmpi_")
+    write_inp(os.path.join(tmp, "miniaero.inp"), **inp)
+    os.makedirs(os.path.join(tmp, "mpi"))
+    procs = []
+    for r in range(nranks):
+        env = dict(os.environ, MINIAERO_MPI_RANK=str(r), MINIAERO_MPI_SIZE=str(nranks),
+                   MINIAERO_MPI_DIR=os.path.join(tmp, "mpi"), OMP_NUM_THREADS="1")
+        env.pop("MINIAERO_DUMP_DIR", None)
+        if dump:
+            d = os.path.join(tmp, "dump%d" % r)
+            os.makedirs(d)
+            env["MINIAERO_DUMP_DIR"] = d
+            env["MINIAERO_DUMP_LABELS"] = labels  # every ghost exchange deep_copies: keep only what is asked for
+        procs.append(subprocess.Popen([exe], cwd=tmp, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    out = []
+    for r, p in enumerate(procs):
+        so, se = p.communicate(timeout=timeout)
+        if p.returncode != 0:
+            for q in procs:
+                if q.poll() is None:
+                    q.kill()
+            raise RuntimeError("reference rank %d failed: %s\n%s" % (r, p.returncode, se[-2000:]))
+        res = os.path.join(tmp, "results.%d" % r)
+        dumps = []
+        if dump:
+            d = os.path.join(tmp, "dump%d" % r)
+            for name in sorted(os.listdir(d)):
+                dumps.append((name.split("_", 1)[1][:-4], read_dump(os.path.join(d, name))))
+        out.append({"stdout": so, "results": np.loadtxt(res, ndmin=2) if os.path.isfile(res) else None, "dumps": dumps,
+                    "workdir": tmp})
     return out
 
 

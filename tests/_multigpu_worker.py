@@ -1,0 +1,72 @@
+"""Worker of tests/test_gpu_multi.py: one process per GPU (torch.distributed.run, NCCL), the block-decomposed
+RK4 step with NCCL halo exchange through the C ABI, checked per rank against the full-precision results of the
+reference's WITH_MPI build (tests/golden/par_*.npz, made by tests/golden/make_golden.py parallel)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+import cases  # noqa: E402
+import parity  # noqa: E402
+import miniaero_b200 as ma  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    comm = ma.HaloComm.from_torch_distributed(local)
+    report = {}
+    for name in sys.argv[1:]:
+        inp, rank_counts, _, rel_tol, floor = cases.PARALLEL[name]
+        if world not in rank_counts:
+            continue
+        g = np.load(os.path.join(parity.GOLDEN, "par_%s_%d.npz" % (name, world)))
+        serial = parity.golden(name) if os.path.isfile(os.path.join(parity.GOLDEN, name + ".npz")) else None
+        for arith, overlap in ((ma.ARITH_STRICT, True), (ma.ARITH_STRICT, False), (ma.ARITH_FAST, True)):
+            for n in (1, 2, 100):
+                opt = ma.Options(**cases.opts_kwargs(dict(inp, ntimesteps=n)))
+                mesh = ma.Parallel3DMesh.from_options(opt, rank, world).fillMeshData()
+                solver = ma.TimeSolverExplicitRK4(mesh, opt, device=local, arith=arith, comm=comm, overlap_halo=overlap)
+                solver.initialize()
+                solver.step(n)
+                sol = solver.solution()
+                ref = g["r%d_step%d" % (rank, n)]
+                linf, l2 = parity.field_errors(sol, ref)
+                entry = {"ulp": parity.max_ulp(sol, ref), "linf": linf, "l2": l2, "launches": solver.timing()["kernel_launches"]}
+                if serial is not None and ("cell_step%d" % n) in serial:
+                    gids = mesh.global_ids[:mesh.num_owned_cells]
+                    entry["linf_vs_single_domain"] = parity.field_errors(sol, serial["cell_step%d" % n][gids])[0]
+                rows = [None] * world
+                dist.all_gather_object(rows, entry)
+                report["%s/arith%d/overlap%d/step%d" % (name, arith, int(overlap), n)] = rows
+                del solver
+        # the reference's own parallel integration test: results.<rank> vs results.<rank>.gold
+        if ("r%d_gold" % rank) in g:
+            import refrun
+            opt = ma.Options(**cases.opts_kwargs(inp))
+            mesh = ma.Parallel3DMesh.from_options(opt, rank, world).fillMeshData()
+            solver = ma.TimeSolverExplicitRK4(mesh, opt, device=local, comm=comm)
+            tmp = "/tmp/miniaero_results_%d.%d" % (os.getpid(), rank)
+            solver.Solve_to(tmp)
+            bad = refrun.numeric_text_diff(np.loadtxt(tmp), g["r%d_gold" % rank], rel_tol, floor)
+            os.remove(tmp)
+            rows = [None] * world
+            dist.all_gather_object(rows, bad)
+            report["%s/gold_diff_lines" % name] = rows
+    if rank == 0:
+        print("MULTIGPU_REPORT " + json.dumps(report))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

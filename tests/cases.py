@@ -39,3 +39,13 @@ def opts_kwargs(inp):
     d = dict(inp)
     d["second_order_space"] = d.pop("second_order")
     return d
+
+
+# multi-rank cases: name -> (inp, [rank counts], reference test dir holding results.<rank>.gold or None, rel_tol, floor)
+PARALLEL = {
+    "3D_Sod_Parallel": (_inp(0, 0.3048, 1.0, 1.0, 0.0, 128, 4, 4, 100, 2e-6, 1, 0), [2, 4], "3D_Sod_Parallel", 1e-3, 1e-6),
+    "FlatPlate_Parallel": (_inp(1, 2.0, 0.002, 1.0, 0.0, 32, 64, 2, 400, 1e-8, 1, 1), [2, 8], "FlatPlate_Parallel", 1e-2, 1e-3),
+    "sod_o2_visc": (EXTRA["sod_o2_visc"], [2, 4, 8], None, 0, 0),
+    "ramp_o2_visc": (_inp(2, 2.0, 2.0, 1.0, 30.0, 32, 16, 8, 100, 1e-5, 1, 1), [2, 4], None, 0, 0),
+    "sod_o1": (_inp(0, 0.3048, 1.0, 1.0, 0.0, 64, 8, 4, 100, 2e-6, 0, 0), [2], None, 0, 0),
+}

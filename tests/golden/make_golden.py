@@ -37,5 +37,27 @@ def main():
         print(name, sorted(out.keys()))
 
 
+def main_parallel():
+    """Per-rank full-precision results of the reference's WITH_MPI build (oracle/_ref/miniAero.cell.mpi over the
+    file-based MPI stand-in) -> tests/golden/par_<case>_<N>.npz; plus the reference's parallel gold files."""
+    for name, (inp, rank_counts, ref_dir, _, _) in cases.PARALLEL.items():
+        for nranks in rank_counts:
+            out = {"nranks": np.array(nranks)}
+            for n in sorted({1, 2, 100, inp["ntimesteps"]}):
+                per_rank = refrun.run_reference_parallel(dict(inp, ntimesteps=n), nranks)
+                for r, o in enumerate(per_rank):
+                    nown = o["results"].shape[0]
+                    out["r%d_step%d" % (r, n)] = refrun.solution_from_dumps(o["dumps"])[:nown]
+            for r in range(nranks):
+                gold = os.path.join(REF_TESTS, ref_dir or "-", "results.%d.gold" % r)
+                if ref_dir and os.path.isfile(gold) and len(os.listdir(os.path.join(REF_TESTS, ref_dir))) == nranks + 3:
+                    out["r%d_gold" % r] = np.loadtxt(gold)
+            np.savez_compressed(os.path.join(HERE, "par_%s_%d.npz" % (name, nranks)), **out)
+            print(name, nranks, len(out))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "parallel":
+        main_parallel()
+    else:
+        main()

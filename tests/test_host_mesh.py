@@ -111,3 +111,22 @@ def test_results_writer_matches_the_reference_text(lib, tmp_path):
     mesh = ma.Parallel3DMesh.from_options(ma.Options(**cases.opts_kwargs(inp))).fillMeshData()
     ma.write_results(str(tmp_path / "results.0"), mesh, refrun.solution_from_dumps(out["dumps"]))
     assert open(tmp_path / "results.0").read() == ref_text
+
+
+@pytest.mark.skipif(not __import__("os").path.isfile(__import__("os").path.join(refrun.REF_DIR, "miniAero.cell.mpi")),
+                    reason="oracle/_ref/miniAero.cell.mpi not built")
+@pytest.mark.parametrize("name,nranks", [("sod_o2_visc", 2), ("sod_o2_visc", 8), ("FlatPlate_Parallel", 8), ("ramp_o2_visc", 4)])
+def test_block_meshes_match_the_reference_mpi_build(lib, name, nranks):
+    """Per rank: owned + ghost cell order, centroids (bit for bit) and owned volumes equal what the reference's
+    WITH_MPI mesh setup (Parallel3DMesh.C:98-174, 306-431) hands its solver."""
+    import miniaero_b200 as ma
+    inp = cases.PARALLEL[name][0]
+    out = refrun.run_reference_parallel(dict(inp, ntimesteps=1), nranks, labels="cell_coordinates,cell_volumes")
+    for r, o in enumerate(out):
+        d = dict(o["dumps"])
+        mesh = ma.Parallel3DMesh.from_options(ma.Options(**cases.opts_kwargs(inp)), r, nranks).fillMeshData()
+        n = mesh.num_owned_cells
+        assert d["cell_coordinates"].shape[0] == n + mesh.num_ghosts, (r, d["cell_coordinates"].shape, n, mesh.num_ghosts)
+        assert o["results"].shape[0] == n
+        assert parity.max_ulp(mesh.cell_coordinates, d["cell_coordinates"]) == 0, r
+        assert parity.max_ulp(mesh.cell_volumes[:n], d["cell_volumes"][:n]) == 0, r

@@ -2,6 +2,8 @@
 (a) pass the reference's own integration tests — its 6-digit gold files, re-encoded in tests/golden/*.npz —
 at the tolerances of tests/<case>/<case>_test.sh, and (b) reproduce, bit for bit, the full-precision golden
 vectors the GPU parity tests compare against (so those vectors provably come from this oracle)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -72,3 +74,41 @@ def test_numeric_text_diff_semantics():
     b[1, 1] = 5.02                        # 0.4 % > 1e-3
     assert refrun.numeric_text_diff(a, b) == 1
     assert refrun.numeric_text_diff(a, b, rel_tol=1e-2) == 0
+
+
+# ---- the parallel oracle: the reference's WITH_MPI build over the file-based MPI stand-in -------------------
+needs_mpi_ref = pytest.mark.skipif(not os.path.isfile(os.path.join(refrun.REF_DIR, "miniAero.cell.mpi")),
+                                   reason="oracle/_ref/miniAero.cell.mpi not built")
+
+
+@needs_mpi_ref
+@pytest.mark.parametrize("name,nranks", [("3D_Sod_Parallel", 4), ("FlatPlate_Parallel", 8)])
+def test_parallel_oracle_passes_the_reference_parallel_gold_files(name, nranks):
+    """tests/3D_Sod_Parallel (mpirun -np 4) and tests/FlatPlate_Parallel (-np 8): per-rank results.<rank> against
+    results.<rank>.gold at the scripts' tolerances, and the committed full-precision per-rank vectors are its bits."""
+    inp, _, _, rel_tol, floor = cases.PARALLEL[name]
+    g = np.load(os.path.join(parity.GOLDEN, "par_%s_%d.npz" % (name, nranks)))
+    out = refrun.run_reference_parallel(inp, nranks)
+    for r, o in enumerate(out):
+        assert refrun.numeric_text_diff(o["results"], g["r%d_gold" % r], rel_tol, floor) == 0, (name, r)
+        nown = o["results"].shape[0]
+        full = refrun.solution_from_dumps(o["dumps"])[:nown]
+        assert parity.max_ulp(full, g["r%d_step%d" % (r, inp["ntimesteps"])]) == 0
+
+
+@needs_mpi_ref
+def test_parallel_oracle_agrees_with_serial_oracle_to_roundoff():
+    """Block seams flip the left/right roles of some faces (owned cell is always elem1), and the Roe flux is not
+    bitwise antisymmetric, so per-rank results differ from the single-domain run by roundoff only."""
+    name, nranks = "sod_o2_visc", 4
+    inp = cases.PARALLEL[name][0]
+    g = np.load(os.path.join(parity.GOLDEN, "par_%s_%d.npz" % (name, nranks)))
+    serial = parity.golden(name)["cell_step100"]
+    import miniaero_b200 as ma
+    worst = 0.0
+    for r in range(nranks):
+        mesh = ma.Parallel3DMesh.from_options(ma.Options(**cases.opts_kwargs(inp)), r, nranks).fillMeshData()
+        gids = mesh.global_ids[:mesh.num_owned_cells]
+        linf, l2 = parity.field_errors(g["r%d_step100" % r], serial[gids])
+        worst = max(worst, linf, l2)
+    assert worst < parity.TOL_100_STEPS, worst
