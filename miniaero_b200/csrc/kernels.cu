@@ -47,17 +47,30 @@ MA_DEV void load_state(const double *__restrict__ base, int stride, int c, doubl
 
 // Face geometry as the kernels see it.  STRICT keeps the caller's tangent and binormal (the reference
 // normalises and uses them, Roe_Flux.h:101-123); FAST needs only the area vector (see roe_flux_normal_only).
+// Where the geometry of a tile's faces lives: component g of tile face e at base[g * cs + e]
+// (STRICT: global SoA [12][n_tile_faces]; FAST: tile-blocked [6][faces rounded up to 16], see layout.h)
+struct TileGeom {
+  const double *base;
+  size_t cs;
+};
+MA_DEV TileGeom tile_geom(const DevMesh &m, const TileInfoDev &T) {
+#ifdef MA_STRICT
+  return {m.face_geom + T.face_start, (size_t)m.n_tile_faces};
+#else
+  return {m.face_geom + (size_t)6 * T.face_start, (size_t)((T.face_count + 15) & ~15)};
+#endif
+}
 #ifdef MA_STRICT
 #define MA_GEOM_XF 9
 struct FaceGeom {
   double n[3], t[3], b[3];
 };
-MA_DEV void load_face_geom(const DevMesh &m, size_t NF, int j, FaceGeom &g) {
+MA_DEV void load_face_geom(const TileGeom &tg, int e, FaceGeom &g) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    g.n[d] = __ldg(m.face_geom + (size_t)(0 + d) * NF + j);
-    g.t[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j);
-    g.b[d] = __ldg(m.face_geom + (size_t)(6 + d) * NF + j);
+    g.n[d] = __ldg(tg.base + (size_t)(0 + d) * tg.cs + e);
+    g.t[d] = __ldg(tg.base + (size_t)(3 + d) * tg.cs + e);
+    g.b[d] = __ldg(tg.base + (size_t)(6 + d) * tg.cs + e);
   }
 }
 MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const FaceGeom &g, double (&flux)[5]) {
@@ -68,9 +81,9 @@ MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const Fa
 struct FaceGeom {
   double n[3];
 };
-MA_DEV void load_face_geom(const DevMesh &m, size_t NF, int j, FaceGeom &g) {
+MA_DEV void load_face_geom(const TileGeom &tg, int e, FaceGeom &g) {
 #pragma unroll
-  for (int d = 0; d < 3; ++d) g.n[d] = __ldg(m.face_geom + (size_t)d * NF + j);
+  for (int d = 0; d < 3; ++d) g.n[d] = __ldg(tg.base + (size_t)d * tg.cs + e);
 }
 MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const FaceGeom &g, double (&flux)[5]) {
   roe_flux_normal_only(Vl, Vr, g.n, flux);
@@ -84,7 +97,7 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
                                                            double *__restrict__ grad, double *__restrict__ lim,
                                                            int tile_begin) {
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
-  const size_t NF = (size_t)m.n_tile_faces;
+  const TileGeom tg = tile_geom(m, T);
   for (int lc = threadIdx.x; lc < T.cell_count; lc += blockDim.x) {
     const int c = T.cell_start + lc;
     double V[5];
@@ -107,12 +120,13 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
     for (int s = 0; s < 6; ++s) {  // slot order == the reference's gather order (GreenGauss.h:255-267)
       const unsigned sf = m.slot_face[(size_t)s * m.slot_stride + c];
       const int side = sf >> 15;
-      const int j = T.face_start + (int)(sf & 0x3fffu);
-      fj[s] = j;
+      const int e = (int)(sf & 0x3fffu);
+      const int j = T.face_start + e;
+      fj[s] = e;
       const int r = __ldg(m.face_right + j);
       double n[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) n[d] = __ldg(m.face_geom + (size_t)d * NF + j);
+      for (int d = 0; d < 3; ++d) n[d] = __ldg(tg.base + (size_t)d * tg.cs + e);
       if (r >= 0) {
         const int nb = side ? __ldg(m.face_left + j) : r;
         double Vn[5];
@@ -201,12 +215,12 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
 #endif
 #pragma unroll
       for (int s = 0; s < 6; ++s) {
-        const int j = fj[s];
+        const int e = fj[s];
         double disp[3];
         double dist = 0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          disp[d] = __ldg(m.face_geom + (size_t)(MA_GEOM_XF + d) * NF + j) - xc[d];  // StencilLimiter.h:425-433
+          disp[d] = __ldg(tg.base + (size_t)(MA_GEOM_XF + d) * tg.cs + e) - xc[d];  // StencilLimiter.h:425-433
           dist += disp[d] * disp[d];
         }
 #pragma unroll
@@ -246,7 +260,7 @@ template <bool SECOND, bool VISCOUS>
 __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
   extern __shared__ double sflux[];
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
-  const size_t NF = (size_t)m.n_tile_faces;
+  const TileGeom tg = tile_geom(m, T);
   const int FS = m.flux_smem_stride;
   const int CS = m.rk_smem_stride;
   const double *__restrict__ V_ = a.V;
@@ -272,7 +286,7 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
     const int l = __ldg(m.face_left + j);
     const int r = __ldg(m.face_right + j);
     FaceGeom G;
-    load_face_geom(m, NF, j, G);
+    load_face_geom(tg, e, G);
     double Vl[5], flux[5];
     load_state(V_, m.stride, l, Vl);
     if (r >= 0) {
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
         double dl[3], dr[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          const double xf = __ldg(m.face_geom + (size_t)(MA_GEOM_XF + d) * NF + j);
+          const double xf = __ldg(tg.base + (size_t)(MA_GEOM_XF + d) * tg.cs + e);
           dl[d] = xf - __ldg(m.cell_xyz + (size_t)d * m.stride + l);
           dr[d] = xf - __ldg(m.cell_xyz + (size_t)d * m.stride + r);
         }
@@ -368,7 +382,7 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
         double xf[3], xc[3], vflux[5];
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          xf[d] = __ldg(m.face_geom + (size_t)(MA_GEOM_XF + d) * NF + j);
+          xf[d] = __ldg(tg.base + (size_t)(MA_GEOM_XF + d) * tg.cs + e);
           xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + l);
         }
         noslip_viscous_flux(Vl, G.n, area_norm, xf, xc, vflux);
@@ -432,263 +446,435 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB) flux_rk_kernel(
 
 #ifndef MA_STRICT
 // ======================================================================================================
-// FAST tile kernels: cell-block tiles staged in shared memory.
-//
-// Every global load of cell data is issued by a thread that owns a whole cell (own cells: coalesced SoA
-// reads with no index indirection; outside cells of cut faces: one gather per cut face), so the per-face
-// gather of 2 x 28 doubles of the reference's compute_face_flux (Flux.h:89-132) never happens.
+// FAST staged tile kernels: the sm_100a bulk-copy engine (cp.async.bulk, "TMA 1-D") moves every contiguous
+// operand run of a tile — geometry of its faces, the SoA records of its own cells, the RK operands — into
+// shared memory, the outside cells of its cut faces follow by 8-byte asynchronous gathers (LDGSTS), and ONE
+// mbarrier collects both.  No thread holds a register or a scoreboard slot for data in flight, and the
+// arithmetic afterwards reads shared memory only (32-bit addressing, immediate offsets).  Several CTAs per
+// SM are resident, so one tile's copy phase runs behind another tile's arithmetic.
 // ======================================================================================================
+MA_DEV unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+MA_DEV void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+MA_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+MA_DEV void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// the calling thread's earlier cp.async copies arrive on the barrier when they land (counted in the init count)
+MA_DEV void mbar_cp_async_arrive(unsigned bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+MA_DEV void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared bulk copy; 16-byte aligned on both sides, bytes a multiple of 16; completes on the mbarrier
+MA_DEV void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+MA_DEV void cp_async8s(unsigned dst, const double *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+
+// Capacity class of a tile: the staged kernels are compiled for a few (cells, faces, cut faces) capacities so
+// that every shared-memory stride is a compile-time constant.
+template <int CELLS, int FACES, int HALO, int GRAD_T, int GRAD_B, int FLUX_T, int FLUX_B>
+struct TileCap {
+  static constexpr int NC = CELLS;                          // own cells
+  static constexpr int FC = (FACES + 15) / 16 * 16;         // tile faces (the copy length is rounded up to 16)
+  static constexpr int HC = HALO;                           // cut faces == staged outside cells
+  static constexpr int LS = (CELLS + 2 + HALO + 1) / 2 * 2; // staged cell list: alignment slack + own + outside
+  static constexpr int RC = CELLS + 2;                      // staged RK operands
+  static constexpr int SC = CELLS + 8;                      // staged slot map (uint16, 16-byte alignment slack)
+  static constexpr int GRAD_THREADS = GRAD_T, GRAD_MINB = GRAD_B, FLUX_THREADS = FLUX_T, FLUX_MINB = FLUX_B;
+};
+using Cap64 = TileCap<64, 240, 96, 64, 8, 96, 6>;      // 4x4x4 bricks
+using Cap128 = TileCap<128, 464, 160, 128, 4, 160, 3>;  // 8x4x4 bricks
+using Cap256 = TileCap<256, 896, 256, 256, 2, 256, 1>;  // 8x8x4 bricks
 
 // ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
-// phase 0: primitives of the tile's cells and of the outside cells of its cut faces -> sV[5][LS]
-// phase 1: thread per cell, neighbours read from shared memory through the tile-local face table
-template <bool SECOND>
-__global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB)
-    grad_limiter_tile_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
-                             double *__restrict__ lim, int tile_begin) {
-  extern __shared__ double smem[];
+// thread per own cell (blockDim >= cells of the tile); neighbours, face normals and centroids from shared memory
+template <bool SECOND, class CAP>
+__global__ void __launch_bounds__(CAP::GRAD_THREADS, CAP::GRAD_MINB)
+    grad_limiter_tma_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
+                            double *__restrict__ lim, int tile_begin) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NG = SECOND ? 6 : 3;  // normal (+ centroid)
+  constexpr int FC = CAP::FC, LS = CAP::LS;
+  double *sG = reinterpret_cast<double *>(smem_raw);  // [NG][FC]
+  double *sV = sG + NG * FC;                          // [5][LS]
+  const unsigned bar = smem_addr(sV + 5 * LS);
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
-  const size_t NF = (size_t)m.n_tile_faces;
-  const int LS = m.local_smem_stride;
+  const int tid = threadIdx.x;
   const int nc = T.cell_count;
-  const int nl = nc + (T.face_count - T.cut_start);
-  double *sV = smem;
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-    const int c = i < nc ? T.cell_start + i : __ldg(m.tile_halo + T.halo_start + (i - nc));
-#pragma unroll
-    for (int k = 0; k < 5; ++k) sV[k * LS + i] = __ldg(V_ + (size_t)k * m.stride + c);
+  const int shift = T.cell_start & 1;
+  const int hb = (shift + nc + 1) & ~1;  // doubles per staged own-cell run == first outside-cell position
+  const int nh = T.face_count - T.cut_start;
+  const unsigned fcp = (unsigned)(T.face_count + 15) & ~15u;
+  if (tid == 0) {
+    mbar_init(bar, blockDim.x + 1);
+    mbar_fence_init();
   }
   __syncthreads();
+  if (tid < 32) {
+    const unsigned gbytes = fcp * 8u, vbytes = (unsigned)hb * 8u;
+    if (tid == 0) mbar_arrive_expect_tx(bar, NG * gbytes + 5 * vbytes);
+    __syncwarp();
+    if (tid < NG) bulk_g2s(smem_addr(sG + tid * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)tid * fcp, gbytes, bar);
+    else if (tid < NG + 5)
+      bulk_g2s(smem_addr(sV + (tid - NG) * LS), V_ + (size_t)(tid - NG) * m.stride + (T.cell_start - shift), vbytes, bar);
+  }
+  for (int h = tid; h < nh; h += blockDim.x) {
+    const int c = __ldg(m.tile_halo + T.halo_start + h);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cp_async8s(smem_addr(sV + k * LS + hb + h), V_ + (size_t)k * m.stride + c);
+  }
+  mbar_cp_async_arrive(bar);
 
-  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
-    const int c = T.cell_start + lc;
-    double V[5];
+  // per-cell operands that only this thread needs: straight to registers, in flight together with the copies
+  const bool active = tid < nc;
+  const int c = T.cell_start + (active ? tid : 0);
+  unsigned sn[6];  // slot_face | slot_nbr << 16
 #pragma unroll
-    for (int k = 0; k < 5; ++k) V[k] = sV[k * LS + lc];
-    const double vol = __ldg(m.cell_vol + c);
-    double g[5][3], mn[5], mx[5];
+  for (int s = 0; s < 6; ++s)
+    sn[s] = (unsigned)__ldg(m.slot_face + (size_t)s * m.slot_stride + c) |
+            ((unsigned)__ldg(m.slot_nbr + (size_t)s * m.slot_stride + c) << 16);
+  const double vol = __ldg(m.cell_vol + c);
+  double xc[3] = {0.0, 0.0, 0.0};
+  if (SECOND) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      g[k][0] = g[k][1] = g[k][2] = 0;
-      mn[k] = mx[k] = V[k];  // min/max over {cell, face neighbours} (StencilLimiter.h:139-140, 272-273)
-    }
-    unsigned sfs[6];
+    for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
+  }
+  mbar_wait(bar, 0);
+  if (!active) return;
+
+  double V[5], g[5][3], mn[5], mx[5];
 #pragma unroll
-    for (int s = 0; s < 6; ++s) sfs[s] = m.slot_face[(size_t)s * m.slot_stride + c];
+  for (int k = 0; k < 5; ++k) {
+    V[k] = sV[k * LS + shift + tid];
+    g[k][0] = g[k][1] = g[k][2] = 0;
+    mn[k] = mx[k] = V[k];  // min/max over {cell, face neighbours} (StencilLimiter.h:139-140, 272-273)
+  }
 #pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      const unsigned sf = sfs[s];
-      const int side = sf >> 15;
-      const int j = T.face_start + (int)(sf & 0x3fffu);
-      const double sgn = side ? -1.0 : 1.0;
-      double sn[3];
+  for (int s = 0; s < 6; ++s) {
+    const int e = (int)(sn[s] & 0x3fffu);
+    const double sgn = (sn[s] & 0x8000u) ? -1.0 : 1.0;
+    const unsigned nb = sn[s] >> 16;
+    double an[3];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) sn[d] = sgn * __ldg(m.face_geom + (size_t)d * NF + j);
-      if (!(sf & 0x4000u)) {
-        const unsigned lr = __ldg(m.face_lr + j);
-        const int nb = side ? (int)(lr & 0xffffu) : (int)(lr >> 16);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const double vn = sV[k * LS + nb];
-          const double sum = V[k] + vn;  // 2 x GreenGauss.h:117; the 0.5/vol factor is applied after the loop
-#pragma unroll
-          for (int d = 0; d < 3; ++d) g[k][d] = fma(sum, sn[d], g[k][d]);
-          if (SECOND) {
-            mn[k] = fmin(mn[k], vn);
-            mx[k] = fmax(mx[k], vn);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const double two_v = 2.0 * V[k];  // GreenGauss.h:186-216
-#pragma unroll
-          for (int d = 0; d < 3; ++d) g[k][d] = fma(two_v, sn[d], g[k][d]);
-        }
-      }
-    }
-    {
-      const double half_rvol = 0.5 * rcp(vol);
-#pragma unroll
-      for (int k = 0; k < 5; ++k)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          g[k][d] *= half_rvol;
-          grad[(size_t)(k * 3 + d) * m.stride + c] = g[k][d];
-        }
-    }
-    if (SECOND) {
-      double xc[3];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
-      double pN[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pD[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
-      double dumax[5], ndumin[5];
+    for (int d = 0; d < 3; ++d) an[d] = sgn * sG[d * FC + e];
+    if (nb != 0xFFFFu) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        dumax[k] = mx[k] - V[k];
-        ndumin[k] = V[k] - mn[k];
-      }
+        const double vn = sV[k * LS + nb];
+        const double sum = V[k] + vn;  // 2 x GreenGauss.h:117; the 0.5/vol factor is applied after the loop
 #pragma unroll
-      for (int s = 0; s < 6; ++s) {
-        const int j = T.face_start + (int)(sfs[s] & 0x3fffu);
-        double disp[3];
-        double dist = 0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          disp[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j) - xc[d];  // StencilLimiter.h:425-433
-          dist = fma(disp[d], disp[d], dist);
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const double dU = disp[0] * g[k][0] + disp[1] * g[k][1] + disp[2] * g[k][2];  // StencilLimiter.h:438-446
-          // VenkatLimiter.h:45-73 with a = |du|, mm = |dumax| or |dumin| by the sign of du and the common factor
-          // du cancelled: phi = (mm^2 + eps2 + 2 a mm) / (mm^2 + eps2 + a (2a + mm)); phi -> 1 as a -> 0
-          const double a = fabs(dU);
-          const double mm = dU > 0.0 ? dumax[k] : ndumin[k];
-          const double base = fma(mm, mm, dist);
-          const double a2 = a + a;
-          const double N = fma(a2, mm, base);
-          const double D = fma(a, a2 + mm, base);
-          venkat_fraction_min(N, D, pN[k], pD[k]);
+        for (int d = 0; d < 3; ++d) g[k][d] = fma(sum, an[d], g[k][d]);
+        if (SECOND) {
+          mn[k] = fmin(mn[k], vn);
+          mx[k] = fmax(mx[k], vn);
         }
       }
+    } else {
 #pragma unroll
-      for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = quot(pN[k], pD[k]);
+      for (int k = 0; k < 5; ++k) {
+        const double two_v = 2.0 * V[k];  // GreenGauss.h:186-216
+#pragma unroll
+        for (int d = 0; d < 3; ++d) g[k][d] = fma(two_v, an[d], g[k][d]);
+      }
     }
+  }
+  {
+    const double half_rvol = 0.5 * rcp(vol);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        g[k][d] *= half_rvol;
+        grad[(size_t)(k * 3 + d) * m.stride + c] = g[k][d];
+      }
+  }
+  if (SECOND) {
+    double pN[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pD[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+    double dumax[5], ndumin[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      dumax[k] = mx[k] - V[k];
+      ndumin[k] = V[k] - mn[k];
+    }
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      const int e = (int)(sn[s] & 0x3fffu);
+      double disp[3];
+      double dist = 0;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        disp[d] = sG[(3 + d) * FC + e] - xc[d];  // StencilLimiter.h:425-433
+        dist = fma(disp[d], disp[d], dist);
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double dU = disp[0] * g[k][0] + disp[1] * g[k][1] + disp[2] * g[k][2];  // StencilLimiter.h:438-446
+        // VenkatLimiter.h:45-73 with a = |du|, mm = |dumax| or |dumin| by the sign of du and the common factor
+        // du cancelled: phi = (mm^2 + eps2 + 2 a mm) / (mm^2 + eps2 + a (2a + mm)); phi -> 1 as a -> 0
+        const double aa = fabs(dU);
+        const double mm = dU > 0.0 ? dumax[k] : ndumin[k];
+        const double base = fma(mm, mm, dist);
+        const double a2 = aa + aa;
+        venkat_fraction_min(fma(a2, mm, base), fma(aa, a2 + mm, base), pN[k], pD[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = quot(pN[k], pD[k]);
   }
 }
 
 // ---- sweep 2: face fluxes + slot-ordered gather + RK stage update -----------------------------------
-// Shared memory S[NC][FS] (component-major, one column per tile face):
-//   phase A  thread per cell (own cells, then the outside cell of every cut face): loads the cell's record
-//            (V 5, grad 15, lim 5, xyz 3) once and, for each of its faces in the tile, stores that side's
-//            limited-extrapolated primitives (Flux.h:109-132) and — viscous — its half of the face stress:
-//            q_i = sum_j tau_ij(grad) a_j, h = grad(T).a  (Viscous_Flux.h:65-98 is linear in the gradient, and
-//            the face gradient is the plain average of the two cell gradients, Flux.h:146-149)
-//   phase B  thread per face: Roe flux of the two staged states (+ viscous flux from the staged halves), or
-//            the boundary-condition flux; the result overwrites the face's column
-//   phase C  thread per cell: gather of the six face fluxes in slot order (Flux.h:216-227), RK update
+// Shared memory: sRec[NREC][RC] cell records (V 5, gradient 15, limiter 5, centroid 3) of the tile's own cells;
+// sG[6][FC] face geometry, overwritten face by face with the flux; sRK[11][RC] volume, Un, Acc of the own
+// cells; sLR[FC] tile-local face connectivity; sSlot[6][SC] slot map.  All of it arrives by bulk copies.
+// The record of the outside cell of a cut face never touches shared memory: the thread that will evaluate that
+// face gathers it straight into registers before it waits for the copies, so the gather's latency hides behind
+// the copies and the per-CTA footprint stays small enough for three resident CTAs per SM.
+//   phase 1  thread per tile face (cut faces first): limited extrapolation of both cell records to the face
+//            (Flux.h:109-132), Roe flux (+ viscous flux), or the boundary-condition flux
+//   phase 2  thread per own cell: gather of the six face fluxes in slot order (Flux.h:216-227), RK update
 template <bool SECOND, bool VISCOUS>
-__global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB)
-    flux_rk_tile_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
-  extern __shared__ double S[];
-  constexpr int SIDE = VISCOUS ? 9 : 5;  // components per side: V'[5] (+ q[3], h)
-  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
-  const size_t NF = (size_t)m.n_tile_faces;
-  const int FS = m.flux_smem_stride;
-  const int nc = T.cell_count;
-  const int njobs = nc + (T.face_count - T.cut_start);
+struct FluxRec {
+  static constexpr bool GRAD = SECOND || VISCOUS;
+  static constexpr int R_G = 5, R_L = R_G + (GRAD ? 15 : 0), R_X = R_L + (SECOND ? 5 : 0), NREC = R_X + (SECOND ? 3 : 0);
+  static constexpr int NGEOM = SECOND ? 6 : 3;  // copied geometry components
+  static constexpr int NGS = SECOND ? 6 : 5;    // staged columns (the flux needs 5)
+};
+template <bool SECOND, bool VISCOUS, class CAP>
+constexpr size_t flux_tma_smem() {
+  using R = FluxRec<SECOND, VISCOUS>;
+  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + 11 * CAP::RC) * 8 + (size_t)CAP::FC * 4 + (size_t)6 * CAP::SC * 2 + 16;
+}
 
-  // ---- phase A
-  for (int i = threadIdx.x; i < njobs; i += blockDim.x) {
-    const bool own = i < nc;
-    const int c = own ? T.cell_start + i : __ldg(m.tile_halo + T.halo_start + (i - nc));
-    double V[5], lm[5], xc[3], g[5][3];
+// a cell record in shared memory (component stride RC) or in registers
+template <bool SECOND, bool VISCOUS, int RC>
+struct SmemRecord {
+  using R = FluxRec<SECOND, VISCOUS>;
+  const double *p;  // sRec + position
+  MA_DEV double v(int k) const { return p[k * RC]; }
+  MA_DEV double g(int k, int d) const { return p[(R::R_G + k * 3 + d) * RC]; }
+  MA_DEV double lim(int k) const { return p[(R::R_L + k) * RC]; }
+  MA_DEV double x(int d) const { return p[(R::R_X + d) * RC]; }
+};
+template <bool SECOND, bool VISCOUS>
+struct RegRecord {
+  using R = FluxRec<SECOND, VISCOUS>;
+  const double (&r)[R::NREC];
+  MA_DEV double v(int k) const { return r[k]; }
+  MA_DEV double g(int k, int d) const { return r[R::R_G + k * 3 + d]; }
+  MA_DEV double lim(int k) const { return r[R::R_L + k]; }
+  MA_DEV double x(int d) const { return r[R::R_X + d]; }
+};
+// one side of an interior face: primitives limited-extrapolated to the face centroid (Flux.h:109-132) and this
+// cell's share of the gradient sum (Flux.h:146-149; rows 1..4, the density gradient is never used)
+template <bool SECOND, bool VISCOUS, bool FIRST, class REC>
+MA_DEV void face_side(const REC &rec, const double (&xf)[3], double (&V)[5], double (&gs)[5][3]) {
+  if (SECOND) {
+    double dx[3];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) V[k] = __ldg(a.V + (size_t)k * m.stride + c);
-    if (SECOND || VISCOUS) {
+    for (int d = 0; d < 3; ++d) dx[d] = xf[d] - rec.x(d);
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 5; ++k) {
+      double g[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) g[k][d] = __ldg(a.grad + (size_t)(k * 3 + d) * m.stride + c);
-    }
-    if (SECOND) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) lm[k] = __ldg(a.lim + (size_t)k * m.stride + c);
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
-    double txx = 0, tyy = 0, tzz = 0, txy = 0, txz = 0, tyz = 0;
-    if (VISCOUS) {  // tau_ij = S_ij - delta_ij div/3 (Viscous_Flux.h:80-90)
-      const double third_div = (g[1][0] + g[2][1] + g[3][2]) * (1.0 / 3.0);
-      txx = g[1][0] - third_div, tyy = g[2][1] - third_div, tzz = g[3][2] - third_div;
-      txy = 0.5 * (g[1][1] + g[2][0]), txz = 0.5 * (g[1][2] + g[3][0]), tyz = 0.5 * (g[2][2] + g[3][1]);
-    }
-    unsigned sfs[6];
-    int nslots = 1;
-    if (own) {
-      nslots = 6;
-#pragma unroll
-      for (int s = 0; s < 6; ++s) sfs[s] = m.slot_face[(size_t)s * m.slot_stride + c];
-    } else {
-      const int e = T.cut_start + (i - nc);
-      const unsigned lr = __ldg(m.face_lr + T.face_start + e);
-      sfs[0] = (unsigned)e | (((lr & 0xffffu) == (unsigned)i) ? 0u : 0x8000u);
-    }
-#pragma unroll
-    for (int s = 0; s < 6; ++s) {
-      if (s < nslots) {
-        const unsigned sf = sfs[s];
-        const int e = (int)(sf & 0x3fffu);
-        const int j = T.face_start + e;
-        double *col = S + ((sf >> 15) ? SIDE * FS : 0) + e;
-        if (sf & 0x4000u) {
-          // boundary face: first order (the *_BC.h functors take the cell state as is); the cell centroid is
-          // parked in the unused right half for NoSlip_BC.h:114-139
-#pragma unroll
-          for (int k = 0; k < 5; ++k) col[k * FS] = V[k];
-#pragma unroll
-          for (int d = 0; d < 3; ++d) col[(SIDE + d) * FS] = xc[d];
-        } else {
-          double dx[3];
-          if (SECOND) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) dx[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j) - xc[d];
-          }
-#pragma unroll
-          for (int k = 0; k < 5; ++k) {
-            double v = V[k];
-            if (SECOND) v = fma(lm[k], dx[0] * g[k][0] + dx[1] * g[k][1] + dx[2] * g[k][2], v);  // Flux.h:114-127
-            col[k * FS] = v;
-          }
-          if (VISCOUS) {
-            double av[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) av[d] = __ldg(m.face_geom + (size_t)d * NF + j);
-            col[5 * FS] = txx * av[0] + txy * av[1] + txz * av[2];
-            col[6 * FS] = txy * av[0] + tyy * av[1] + tyz * av[2];
-            col[7 * FS] = txz * av[0] + tyz * av[1] + tzz * av[2];
-            col[8 * FS] = g[4][0] * av[0] + g[4][1] * av[1] + g[4][2] * av[2];
-          }
-        }
+      for (int d = 0; d < 3; ++d) {
+        g[d] = rec.g(k, d);
+        if (VISCOUS && k > 0) gs[k][d] = FIRST ? g[d] : gs[k][d] + g[d];
       }
+      const double t = fma(dx[2], g[2], fma(dx[1], g[1], dx[0] * g[0]));  // Flux.h:114-121
+      V[k] = fma(t, rec.lim(k), rec.v(k));                               // Flux.h:124-127
     }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) V[k] = rec.v(k);
+    if (VISCOUS) {
+#pragma unroll
+      for (int k = 1; k < 5; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) gs[k][d] = FIRST ? rec.g(k, d) : gs[k][d] + rec.g(k, d);
+    }
+  }
+}
+// Roe flux (Roe_Flux.h:49-265) minus the Newtonian viscous flux (Viscous_Flux.h:65-98) at the face state
+// 0.5 (Vl + Vr) (Flux.h:142-143) with gs = 2 x face gradient
+template <bool VISCOUS>
+MA_DEV void interior_flux(const double (&Vl)[5], const double (&Vr)[5], const double (&gs)[5][3], const FaceGeom &G,
+                          double (&flux)[5]) {
+  face_roe_flux(Vl, Vr, G, flux);
+  if (VISCOUS) {
+    const double third_div = (gs[1][0] + gs[2][1] + gs[3][2]) * (1.0 / 3.0);
+    const double txx = gs[1][0] - third_div, tyy = gs[2][1] - third_div, tzz = gs[3][2] - third_div;
+    const double txy = 0.5 * (gs[1][1] + gs[2][0]), txz = 0.5 * (gs[1][2] + gs[3][0]);
+    const double tyz = 0.5 * (gs[2][2] + gs[3][1]);
+    const double q0 = txx * G.n[0] + txy * G.n[1] + txz * G.n[2];
+    const double q1 = txy * G.n[0] + tyy * G.n[1] + tyz * G.n[2];
+    const double q2 = txz * G.n[0] + tyz * G.n[1] + tzz * G.n[2];
+    const double hh = gs[4][0] * G.n[0] + gs[4][1] * G.n[1] + gs[4][2] * G.n[2];
+    const double mu = compute_viscosity(0.5 * (Vl[4] + Vr[4]));
+    const double uq = (Vl[1] + Vr[1]) * q0 + (Vl[2] + Vr[2]) * q1 + (Vl[3] + Vr[3]) * q2;
+    flux[1] -= mu * q0;
+    flux[2] -= mu * q1;
+    flux[3] -= mu * q2;
+    flux[4] -= fma(0.5 * mu, uq, 0.5 * compute_thermal_conductivity(mu) * hh);
+  }
+}
+
+template <bool SECOND, bool VISCOUS, class CAP>
+__global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
+    flux_rk_tma_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using R = FluxRec<SECOND, VISCOUS>;
+  constexpr int FC = CAP::FC, RC = CAP::RC, SC = CAP::SC;
+  constexpr int R_G = R::R_G, R_L = R::R_L, R_X = R::R_X, NREC = R::NREC, NGEOM = R::NGEOM;
+  using SRec = SmemRecord<SECOND, VISCOUS, RC>;
+  using RRec = RegRecord<SECOND, VISCOUS>;
+  double *sRec = reinterpret_cast<double *>(smem_raw);                   // [NREC][RC]
+  double *sG = sRec + NREC * RC;                                         // [NGS][FC]
+  double *sRK = sG + R::NGS * FC;                                        // [11][RC]
+  unsigned *sLR = reinterpret_cast<unsigned *>(sRK + 11 * RC);           // [FC]
+  unsigned short *sSlot = reinterpret_cast<unsigned short *>(sLR + FC);  // [6][SC]
+  const unsigned bar = smem_addr(sSlot + 6 * SC);
+  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
+  const int tid = threadIdx.x;
+  const int nc = T.cell_count, nf = T.face_count;
+  const int shift = T.cell_start & 1;
+  const int hb = (shift + nc + 1) & ~1;  // doubles per staged own-cell run; positions >= hb are outside cells
+  const int nh = (m.exp_flags & 1) ? 0 : nf - T.cut_start;
+  const unsigned fcp = (unsigned)(nf + 15) & ~15u;
+  const int sshift = T.cell_start & 7;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
   }
   __syncthreads();
 
-  // ---- phase B
-  for (int e = threadIdx.x; e < T.face_count; e += blockDim.x) {
-    const int j = T.face_start + e;
-    const unsigned r16 = __ldg(m.face_lr + j) >> 16;
-    FaceGeom G;
-    load_face_geom(m, NF, j, G);
-    double Vl[5], Vr[5], flux[5];
-#pragma unroll
-    for (int k = 0; k < 5; ++k) Vl[k] = S[k * FS + e];
-    if (r16 < 0xFFF0u) {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) Vr[k] = S[(SIDE + k) * FS + e];
-      face_roe_flux(Vl, Vr, G, flux);
-      if (VISCOUS) {
-        // Viscous_Flux.h:65-98 at the face state 0.5 (Vl' + Vr') (Flux.h:142-143) from the staged halves
-        const double Tf = 0.5 * (Vl[4] + Vr[4]);
-        const double mu = compute_viscosity(Tf);
-        const double kappa_half = 0.5 * compute_thermal_conductivity(mu);
-        const double q0 = S[5 * FS + e] + S[(SIDE + 5) * FS + e];
-        const double q1 = S[6 * FS + e] + S[(SIDE + 6) * FS + e];
-        const double q2 = S[7 * FS + e] + S[(SIDE + 7) * FS + e];
-        const double hh = S[8 * FS + e] + S[(SIDE + 8) * FS + e];
-        const double half_mu = 0.5 * mu;
-        const double uq = (Vl[1] + Vr[1]) * q0 + (Vl[2] + Vr[2]) * q1 + (Vl[3] + Vr[3]) * q2;  // 2 u_face . q
-        flux[1] -= mu * q0;
-        flux[2] -= mu * q1;
-        flux[3] -= mu * q2;
-        flux[4] -= fma(half_mu, uq, kappa_half * hh);
+  // ---- copy phase
+  if (tid < 32) {
+    const unsigned vbytes = (unsigned)hb * 8u, gbytes = fcp * 8u, lbytes = fcp * 4u;
+    const unsigned sbytes = (unsigned)((sshift + nc + 7) & ~7) * 2u;
+    const int nrk = 1 + (a.kind != 2 ? 5 : 0) + (a.kind != 0 ? 5 : 0);
+    if (tid == 0) mbar_arrive_expect_tx(bar, (NREC + nrk) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes);
+    __syncwarp();
+    const size_t c0 = (size_t)(T.cell_start - shift);
+    constexpr int NCOPY = NREC + 11 + NGEOM + 1 + 6;
+    for (int i = tid; i < NCOPY; i += 32) {
+      if (i < NREC) {
+        const double *base = i < R_G   ? a.V + (size_t)i * m.stride
+                             : i < R_L ? a.grad + (size_t)(i - R_G) * m.stride
+                             : i < R_X ? a.lim + (size_t)(i - R_L) * m.stride
+                                       : m.cell_xyz + (size_t)(i - R_X) * m.stride;
+        bulk_g2s(smem_addr(sRec + i * RC), base + c0, vbytes, bar);
+      } else if (i < NREC + 11) {
+        const int j = i - NREC;
+        if (j == 0)
+          bulk_g2s(smem_addr(sRK), m.cell_vol + c0, vbytes, bar);
+        else if (j < 6) {
+          if (a.kind != 2) bulk_g2s(smem_addr(sRK + j * RC), a.Un + (size_t)(j - 1) * m.stride + c0, vbytes, bar);
+        } else {
+          if (a.kind != 0) bulk_g2s(smem_addr(sRK + j * RC), a.Acc + (size_t)(j - 6) * m.stride + c0, vbytes, bar);
+        }
+      } else if (i < NREC + 11 + NGEOM) {
+        const int gi = i - NREC - 11;
+        bulk_g2s(smem_addr(sG + gi * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)gi * fcp, gbytes, bar);
+      } else if (i == NREC + 11 + NGEOM) {
+        bulk_g2s(smem_addr(sLR), m.face_lr + T.face_start, lbytes, bar);
+      } else {
+        const int s = i - (NREC + 11 + NGEOM + 1);
+        bulk_g2s(smem_addr(sSlot + s * SC), m.slot_face + (size_t)s * m.slot_stride + (T.cell_start - sshift), sbytes, bar);
       }
+    }
+  }
+  // the outside-cell record of this thread's cut face: registers, in flight together with the copies
+  double orec[NREC];
+  auto gather_outside = [&](int h) {
+    const int c = __ldg(m.tile_halo + T.halo_start + h);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) orec[k] = __ldg(a.V + (size_t)k * m.stride + c);
+    if (R::GRAD) {
+#pragma unroll
+      for (int k = 0; k < 15; ++k) orec[R_G + k] = __ldg(a.grad + (size_t)k * m.stride + c);
+    }
+    if (SECOND) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) orec[R_L + k] = __ldg(a.lim + (size_t)k * m.stride + c);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) orec[R_X + d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
+    }
+  };
+  if (tid < nh) gather_outside(tid);
+  mbar_wait(bar, 0);
+
+  // ---- phase 1: one flux per tile face.  Work item w: cut face cut_start + w for w < nh, closed / boundary face
+  // w - nh otherwise; thread t takes w = t, t + blockDim, ...
+  const int nwork = (m.exp_flags & 2) ? 0 : nf;
+  int w = tid;
+  for (; w < nh && w < nwork; w += blockDim.x) {  // cut faces (one per thread unless blockDim < cut faces of the tile)
+    if (w != tid) gather_outside(w);
+    const int e = T.cut_start + w;
+    const unsigned lr = sLR[e];
+    const int pl = (int)(lr & 0xffffu), pr = (int)(lr >> 16);
+    FaceGeom G;
+    double xf[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      G.n[d] = sG[d * FC + e];
+      xf[d] = SECOND ? sG[(3 + d) * FC + e] : 0.0;
+    }
+    double Vl[5], Vr[5], gs[5][3], flux[5];
+    const RRec outside{orec};
+    // the outside record first: its registers are free before the own cell's record is read
+    if (pr >= hb) {  // outside cell on the right
+      face_side<SECOND, VISCOUS, true>(outside, xf, Vr, gs);
+      face_side<SECOND, VISCOUS, false>(SRec{sRec + pl}, xf, Vl, gs);
     } else {
-      const int type = (int)(0xFFFFu - r16);
+      face_side<SECOND, VISCOUS, true>(outside, xf, Vl, gs);
+      face_side<SECOND, VISCOUS, false>(SRec{sRec + pr}, xf, Vr, gs);
+    }
+    interior_flux<VISCOUS>(Vl, Vr, gs, G, flux);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];  // this thread's own column: geometry is dead
+  }
+  for (; w < nwork; w += blockDim.x) {  // closed and boundary faces
+    const int e = w - nh;
+    const unsigned lr = sLR[e];
+    const int pl = (int)(lr & 0xffffu);
+    const unsigned pr = lr >> 16;
+    FaceGeom G;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) G.n[d] = sG[d * FC + e];
+    double flux[5];
+    if (pr < 0xFFF0u) {
+      // interior face: Flux.h:89-160
+      double xf[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xf[d] = SECOND ? sG[(3 + d) * FC + e] : 0.0;
+      double Vl[5], Vr[5], gs[5][3];
+      face_side<SECOND, VISCOUS, true>(SRec{sRec + pl}, xf, Vl, gs);
+      face_side<SECOND, VISCOUS, false>(SRec{sRec + (int)pr}, xf, Vr, gs);
+      interior_flux<VISCOUS>(Vl, Vr, gs, G, flux);
+    } else {
+      // boundary face, always first order (Extrapolate_BC.h, Tangent_BC.h, Inflow_BC.h, NoSlip_BC.h)
+      const int type = (int)(0xFFFFu - pr);
+      double Vl[5], Vr[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) Vl[k] = sRec[k * RC + pl];
       double area_norm = 0;
-      if (type == 0) {  // Extrapolate_BC.h:82-83
+      if (type == 0) {  // Extrapolate_BC.h:82-83: Roe(V, V)
 #pragma unroll
         for (int k = 0; k < 5; ++k) Vr[k] = Vl[k];
       } else if (type == 2) {  // Inflow_BC.h:84-90
@@ -700,54 +886,57 @@ __global__ void __launch_bounds__(MA_FLUX_THREADS, MA_FLUX_MINB)
         mirror_state(Vl, G.n, Vr, area_norm);
       }
       face_roe_flux(Vl, Vr, G, flux);
-      if (type == 3) {  // NoSlip_BC.h:114-139
+      if (type == 3) {  // NoSlip_BC.h:114-139 — viscous wall flux regardless of options.viscous
         double xf[3], xc[3], vflux[5];
+        const int cg = T.cell_start + (pl - shift);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          xf[d] = __ldg(m.face_geom + (size_t)(3 + d) * NF + j);
-          xc[d] = S[(SIDE + d) * FS + e];
+          xf[d] = SECOND ? sG[(3 + d) * FC + e]
+                         : __ldg(m.face_geom + (size_t)6 * T.face_start + (size_t)(3 + d) * fcp + e);
+          xc[d] = SECOND ? sRec[(R_X + d) * RC + pl] : __ldg(m.cell_xyz + (size_t)d * m.stride + cg);
         }
         noslip_viscous_flux(Vl, G.n, area_norm, xf, xc, vflux);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) flux[k] -= vflux[k];
+        for (int k = 0; k < 5; ++k) flux[k] -= vflux[k];  // slot = -iflux + vflux == -(iflux - vflux)
       }
     }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) S[k * FS + e] = flux[k];
+    for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];
   }
   __syncthreads();
 
-  // ---- phase C
-  for (int lc = threadIdx.x; lc < nc; lc += blockDim.x) {
+  // ---- phase 2: slot-ordered gather, residual, RK update; the next stage state is stored as primitives
+  for (int lc = tid; lc < nc; lc += blockDim.x) {
     const int c = T.cell_start + lc;
-    const double dtv = a.dt * rcp(__ldg(m.cell_vol + c));
-    double R[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int p = shift + lc;
+    const double dtv = a.dt * rcp(sRK[p]);
+    double Rs[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
-      const unsigned sf = m.slot_face[(size_t)s * m.slot_stride + c];
+      const unsigned sf = sSlot[s * SC + sshift + lc];
       const int e = (int)(sf & 0x3fffu);
-      const double sg = (sf >> 15) ? dtv : -dtv;  // Flux.h:172-178: left slot holds -flux, right slot +flux
+      const double sg = (sf & 0x8000u) ? dtv : -dtv;  // Flux.h:172-178: left slot holds -flux, right slot +flux
 #pragma unroll
-      for (int k = 0; k < 5; ++k) R[k] = fma(sg, S[k * FS + e], R[k]);
+      for (int k = 0; k < 5; ++k) Rs[k] = fma(sg, sG[k * FC + e], Rs[k]);
     }
-    double Wn[5];
+    double Wn[5];  // conservative state the next stage is evaluated at (or the new solution)
     if (a.kind == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double w = a.Un[(size_t)k * m.stride + c];
-        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, R[k], w);
-        Wn[k] = fma(a.alpha_next, R[k], w);
+        const double w0 = sRK[(1 + k) * RC + p];
+        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], w0);
+        Wn[k] = fma(a.alpha_next, Rs[k], w0);
       }
     } else if (a.kind == 1) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, R[k], a.Acc[(size_t)k * m.stride + c]);
-        Wn[k] = fma(a.alpha_next, R[k], a.Un[(size_t)k * m.stride + c]);
+        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], sRK[(6 + k) * RC + p]);
+        Wn[k] = fma(a.alpha_next, Rs[k], sRK[(1 + k) * RC + p]);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        Wn[k] = fma(a.beta, R[k], a.Acc[(size_t)k * m.stride + c]);
+        Wn[k] = fma(a.beta, Rs[k], sRK[(6 + k) * RC + p]);
         a.Un[(size_t)k * m.stride + c] = Wn[k];
       }
     }
@@ -847,40 +1036,119 @@ static size_t gather_flux_smem(const DevMesh &m) {
   return ((size_t)5 * m.flux_smem_stride + (size_t)11 * m.rk_smem_stride) * sizeof(double);
 }
 #ifdef MA_STRICT
-size_t grad_smem_bytes(const DevMesh &) { return 0; }
+int pick_tile_class(int, int, int) { return -1; }
+int tile_class_threads(int, int) { return 0; }
+size_t grad_smem_bytes(const DevMesh &, bool) { return 0; }
 size_t flux_smem_bytes(const DevMesh &m, bool, bool) { return gather_flux_smem(m); }
 #else
-size_t grad_smem_bytes(const DevMesh &m) {
-  return m.grad_variant == 1 ? (size_t)5 * m.local_smem_stride * sizeof(double) : 0;
+template <class CAP>
+static bool cap_fits(int cells, int faces, int halo) {
+  return cells <= CAP::NC && faces <= CAP::FC && halo <= CAP::HC;
 }
-size_t flux_smem_bytes(const DevMesh &m, bool, bool viscous) {
+int pick_tile_class(int cells, int faces, int halo) {
+  if (cap_fits<Cap64>(cells, faces, halo)) return 0;
+  if (cap_fits<Cap128>(cells, faces, halo)) return 1;
+  if (cap_fits<Cap256>(cells, faces, halo)) return 2;
+  return -1;
+}
+int tile_class_threads(int cls, int which) {
+  switch (cls) {
+    case 0: return which ? Cap64::FLUX_THREADS : Cap64::GRAD_THREADS;
+    case 1: return which ? Cap128::FLUX_THREADS : Cap128::GRAD_THREADS;
+    case 2: return which ? Cap256::FLUX_THREADS : Cap256::GRAD_THREADS;
+  }
+  return 0;
+}
+template <class CAP>
+static size_t grad_tma_smem(bool second) {
+  return (size_t)((second ? 6 : 3) * CAP::FC + 5 * CAP::LS) * 8 + 16;
+}
+template <class CAP>
+static size_t flux_tma_smem_rt(bool second, bool viscous) {
+  return second ? (viscous ? flux_tma_smem<true, true, CAP>() : flux_tma_smem<true, false, CAP>())
+                : (viscous ? flux_tma_smem<false, true, CAP>() : flux_tma_smem<false, false, CAP>());
+}
+size_t grad_smem_bytes(const DevMesh &m, bool second) {
+  if (m.grad_variant != 1) return 0;
+  switch (m.tile_class) {
+    case 0: return grad_tma_smem<Cap64>(second);
+    case 1: return grad_tma_smem<Cap128>(second);
+    case 2: return grad_tma_smem<Cap256>(second);
+  }
+  return 0;
+}
+size_t flux_smem_bytes(const DevMesh &m, bool second, bool viscous) {
   if (m.flux_variant != 1) return gather_flux_smem(m);
-  return (size_t)(viscous ? 18 : 10) * m.flux_smem_stride * sizeof(double);
+  switch (m.tile_class) {
+    case 0: return flux_tma_smem_rt<Cap64>(second, viscous);
+    case 1: return flux_tma_smem_rt<Cap128>(second, viscous);
+    case 2: return flux_tma_smem_rt<Cap256>(second, viscous);
+  }
+  return gather_flux_smem(m);
+}
+template <class CAP>
+static cudaError_t launch_grad_tma(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
+                                   int tile_begin, int ntiles, cudaStream_t st) {
+  const size_t smem = grad_tma_smem<CAP>(second);
+  if (second)
+    grad_limiter_tma_kernel<true, CAP><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin);
+  else
+    grad_limiter_tma_kernel<false, CAP><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin);
+  return cudaGetLastError();
+}
+template <class CAP>
+static cudaError_t launch_flux_tma(const DevMesh &m, const StageArgs &a, bool second, bool viscous, int tile_begin,
+                                   int ntiles, int threads, cudaStream_t st) {
+  if (threads <= 0 || threads > CAP::FLUX_THREADS) threads = CAP::FLUX_THREADS;
+  if (second && viscous)
+    flux_rk_tma_kernel<true, true, CAP><<<ntiles, threads, flux_tma_smem<true, true, CAP>(), st>>>(m, a, tile_begin);
+  else if (second)
+    flux_rk_tma_kernel<true, false, CAP><<<ntiles, threads, flux_tma_smem<true, false, CAP>(), st>>>(m, a, tile_begin);
+  else if (viscous)
+    flux_rk_tma_kernel<false, true, CAP><<<ntiles, threads, flux_tma_smem<false, true, CAP>(), st>>>(m, a, tile_begin);
+  else
+    flux_rk_tma_kernel<false, false, CAP><<<ntiles, threads, flux_tma_smem<false, false, CAP>(), st>>>(m, a, tile_begin);
+  return cudaGetLastError();
+}
+template <class CAP>
+static cudaError_t prepare_tma() {
+  cudaError_t e;
+#define MA_SET(K, BYTES)                                                                   \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));  \
+  if (e != cudaSuccess) return e;
+  MA_SET((grad_limiter_tma_kernel<true, CAP>), grad_tma_smem<CAP>(true))
+  MA_SET((grad_limiter_tma_kernel<false, CAP>), grad_tma_smem<CAP>(false))
+  MA_SET((flux_rk_tma_kernel<true, true, CAP>), (flux_tma_smem<true, true, CAP>()))
+  MA_SET((flux_rk_tma_kernel<true, false, CAP>), (flux_tma_smem<true, false, CAP>()))
+  MA_SET((flux_rk_tma_kernel<false, true, CAP>), (flux_tma_smem<false, true, CAP>()))
+  MA_SET((flux_rk_tma_kernel<false, false, CAP>), (flux_tma_smem<false, false, CAP>()))
+#undef MA_SET
+  return cudaSuccess;
 }
 #endif
 
 cudaError_t launch_grad_limiter(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                 int tile_begin, int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
-  const size_t smem = grad_smem_bytes(m);
 #ifndef MA_STRICT
   if (m.grad_variant == 1) {
-    if (second)
-      grad_limiter_tile_kernel<true><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
-    else
-      grad_limiter_tile_kernel<false><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
-    return cudaGetLastError();
+    switch (m.tile_class) {
+      case 0: return launch_grad_tma<Cap64>(m, V, grad, lim, second, tile_begin, ntiles, st);
+      case 1: return launch_grad_tma<Cap128>(m, V, grad, lim, second, tile_begin, ntiles, st);
+      case 2: return launch_grad_tma<Cap256>(m, V, grad, lim, second, tile_begin, ntiles, st);
+    }
   }
 #endif
   if (second)
-    grad_limiter_kernel<true><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
+    grad_limiter_kernel<true><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
   else
-    grad_limiter_kernel<false><<<ntiles, threads, smem, st>>>(m, V, grad, lim, tile_begin);
+    grad_limiter_kernel<false><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
   return cudaGetLastError();
 }
 
-cudaError_t flux_rk_prepare(int smem_bytes) {
+cudaError_t flux_rk_prepare(const DevMesh &m, int smem_bytes) {
   cudaError_t e;
+  (void)m;
 #define MA_SET(K)                                                                          \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);    \
   if (e != cudaSuccess) return e;
@@ -888,35 +1156,30 @@ cudaError_t flux_rk_prepare(int smem_bytes) {
   MA_SET((flux_rk_kernel<false, true>))
   MA_SET((flux_rk_kernel<true, false>))
   MA_SET((flux_rk_kernel<true, true>))
-#ifndef MA_STRICT
-  MA_SET((flux_rk_tile_kernel<false, false>))
-  MA_SET((flux_rk_tile_kernel<false, true>))
-  MA_SET((flux_rk_tile_kernel<true, false>))
-  MA_SET((flux_rk_tile_kernel<true, true>))
-  MA_SET((grad_limiter_tile_kernel<false>))
-  MA_SET((grad_limiter_tile_kernel<true>))
-#endif
 #undef MA_SET
+#ifndef MA_STRICT
+  switch (m.tile_class) {
+    case 0: return prepare_tma<Cap64>();
+    case 1: return prepare_tma<Cap128>();
+    case 2: return prepare_tma<Cap256>();
+  }
+#endif
   return cudaSuccess;
 }
 
 cudaError_t launch_flux_rk(const DevMesh &m, const StageArgs &a, bool second, bool viscous, int tile_begin,
                            int ntiles, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
-  const size_t smem = flux_smem_bytes(m, second, viscous);
 #ifndef MA_STRICT
   if (m.flux_variant == 1) {
-    if (second && viscous)
-      flux_rk_tile_kernel<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
-    else if (second)
-      flux_rk_tile_kernel<true, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
-    else if (viscous)
-      flux_rk_tile_kernel<false, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
-    else
-      flux_rk_tile_kernel<false, false><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
-    return cudaGetLastError();
+    switch (m.tile_class) {
+      case 0: return launch_flux_tma<Cap64>(m, a, second, viscous, tile_begin, ntiles, threads, st);
+      case 1: return launch_flux_tma<Cap128>(m, a, second, viscous, tile_begin, ntiles, threads, st);
+      case 2: return launch_flux_tma<Cap256>(m, a, second, viscous, tile_begin, ntiles, threads, st);
+    }
   }
 #endif
+  const size_t smem = gather_flux_smem(m);
   if (second && viscous)
     flux_rk_kernel<true, true><<<ntiles, threads, smem, st>>>(m, a, tile_begin);
   else if (second)

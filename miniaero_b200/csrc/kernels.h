@@ -19,13 +19,17 @@ struct DevMesh {
   long n_tile_faces;                   // component stride of face_geom
   int flux_smem_stride;                // per-component stride of the shared-memory face staging (>= faces of a tile)
   int rk_smem_stride;                  // per-component stride of the staged RK operands (>= cells of a tile)
-  int grad_variant, flux_variant;      // FAST kernels: 0 = gather kernels, 1 = shared-memory tile kernels
-  int local_smem_stride;               // per-component stride of the shared-memory cell staging (>= cells + cut faces)
+  int grad_variant, flux_variant;      // FAST kernels: 0 = gather kernels, 1 = bulk-copy (TMA) staged tile kernels
+  int exp_flags;                       // experiment switches (MINIAERO_EXP), 0 in production
+  int tile_class;                      // capacity class of the staged tile kernels (kernels.cu: TileClass), -1: none fits
+  int max_tile_cells, max_tile_faces, max_tile_halo, max_tile_local;
   const TileInfoDev *tiles;
   const double *cell_xyz;              // [3][stride]
   const double *cell_vol;              // [stride]
   const uint16_t *slot_face;           // [6][slot_stride]
-  const double *face_geom;             // STRICT [12][n_tile_faces]: normal, tangent, binormal, centroid; FAST [6]: normal, centroid
+  const uint16_t *slot_nbr;            // [6][slot_stride] staged position of the cell across each slot (FAST)
+  const double *face_geom;             // STRICT [12][n_tile_faces]: normal, tangent, binormal, centroid;
+                                       // FAST tile-blocked [tile][6][faces of the tile rounded up to 16]: normal, centroid
   const int *face_left, *face_right;   // [n_tile_faces] renumbered cell ids (STRICT kernels only)
   const uint32_t *face_lr;             // [n_tile_faces] tile-local left | right << 16 (boundary: 0xFFFF - type)
   const int *tile_halo;                // outside cell of every cut face, tile after tile
@@ -53,10 +57,14 @@ struct StageArgs {
   /* Flux.h:52-229 + the four *_BC.h + TimeSolverExplicitRK4.h:106-128 fused */                                      \
   cudaError_t launch_flux_rk(const ma::DevMesh &m, const ma::StageArgs &a, bool second, bool viscous,                \
                              int tile_begin, int ntiles, int threads, cudaStream_t st);                              \
-  cudaError_t flux_rk_prepare(int smem_bytes);                                                                       \
+  cudaError_t flux_rk_prepare(const ma::DevMesh &m, int smem_bytes);                                                                     \
   /* shared memory per CTA of the two stage kernels for this mesh */                                                 \
-  size_t grad_smem_bytes(const ma::DevMesh &m);                                                                      \
-  size_t flux_smem_bytes(const ma::DevMesh &m, bool second, bool viscous);                                                                       \
+  size_t grad_smem_bytes(const ma::DevMesh &m, bool second);                                                         \
+  size_t flux_smem_bytes(const ma::DevMesh &m, bool second, bool viscous);                                           \
+  /* smallest capacity class of the staged tile kernels that holds every tile of the mesh, or -1 */                  \
+  int pick_tile_class(int max_cells, int max_faces, int max_halo);                                                   \
+  /* threads per CTA the staged kernels of that class want (0: caller's choice) */                                   \
+  int tile_class_threads(int tile_class, int which);                                                                 \
   /* GasModel.h:70-90 over the owned cells: conservative Un -> primitives V */                                       \
   cudaError_t launch_primitives(const ma::DevMesh &m, const double *Un, double *V, cudaStream_t st);                 \
   /* Initial_Conditions.h:38-133 */                                                                                  \

@@ -251,6 +251,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   for (long t = 0; t < n_tiles; ++t)
     if (raw[t].boundary) order.push_back(t);
   L.n_tiles = (int)n_tiles;
+  for (long t = 0; t < n_tiles; ++t) L.max_tile_cells_real = std::max(L.max_tile_cells_real, raw[t].count);
   L.tiles.resize(n_tiles);
   L.new2old.resize(n_cells);
   L.old2new.resize(n_cells);
@@ -308,8 +309,8 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
     return on < T.cell_start || on >= T.cell_start + T.cell_count;
   };
   std::vector<long> fstart(n_tiles + 1, 0), hstart(n_tiles + 1, 0);
-  int max_faces = 0, max_local = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_faces, max_local)
+  int max_faces = 0, max_local = 0, max_halo = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : max_faces, max_local, max_halo)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
     int cnt = 0, cut = 0;
@@ -322,12 +323,14 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
     L.tiles[k].face_count = cnt;
     L.tiles[k].cut_start = cnt - cut;
     max_faces = std::max(max_faces, cnt);
-    max_local = std::max(max_local, T.cell_count + cut);
+    max_local = std::max(max_local, round_up((T.cell_start & 1) + T.cell_count, 2) + cut);
+    max_halo = std::max(max_halo, cut);
   }
   if (max_faces >= 16384) return ma_set_error(MA_ERR_INVALID, "tile has more than 16383 faces; use smaller tile_dims");
-  if (max_local >= 0xFFF0) return ma_set_error(MA_ERR_INVALID, "tile has too many cells + cut faces; use smaller tile_dims");
+  if (max_local >= 0xFFF0 - 2) return ma_set_error(MA_ERR_INVALID, "tile has too many cells + cut faces; use smaller tile_dims");
   L.max_tile_faces = max_faces;
   L.max_tile_local = max_local;
+  L.max_tile_halo = max_halo;
   long real = 0;
   for (long k = 0; k < n_tiles; ++k) {
     L.tiles[k].face_start = (int)fstart[k];
@@ -346,16 +349,26 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.face_left.assign(NF, 0);
   L.face_right.assign(NF, 0);
   L.face_lr.assign(NF, 0);
+  L.slot_nbr.assign((size_t)6 * L.slot_stride, 0xFFFF);
   L.tile_halo.assign((size_t)hstart[n_tiles], 0);
+  const char *fo_env = getenv("MINIAERO_FACE_ORDER");
+  const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
+    const size_t fcp = (size_t)round_up(T.face_count, 16);
+    const int shift = T.cell_start & 1, halo_base = round_up(shift + T.cell_count, 2);
     int e_closed = 0, e_cut = T.cut_start;
     // closed / boundary faces first, cut faces last; each group in (cell, slot) order: the face sweep then
     // walks cells in order and every cell's data is touched within a short window
-    for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c) {
+    // face order inside each group: by slot (direction), then by cell — consecutive faces then read consecutive
+    // own cells and consecutive neighbours (conflict-free shared-memory banks in the staged kernels);
+    // MINIAERO_FACE_ORDER=cell keeps (cell, slot) order (the gather kernels' L1 locality)
+    for (int it = 0; it < 6 * T.cell_count; ++it) {
+      const int c = T.cell_start + (by_cell ? it / 6 : it % T.cell_count);
+      const int s = by_cell ? it % 6 : it / T.cell_count;
       const int oldc = L.new2old[c];
-      for (int s = 0; s < 6; ++s) {
+      {
         if (!emits(T, c, s)) continue;
         const bool cut = is_cut(T, c, s);
         const int e = cut ? e_cut++ : e_closed++;
@@ -367,12 +380,16 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
         const double *fn = src.f->face_normal + 3 * fi, *ft = src.f->face_tangent + 3 * fi,
                      *fb = src.f->face_binormal + 3 * fi;
         for (int d = 0; d < 3; ++d) {
-          L.face_geom[(0 + d) * NF + j] = fn[d];
           if (with_tangents) {
+            L.face_geom[(0 + d) * NF + j] = fn[d];
             L.face_geom[(3 + d) * NF + j] = ft[d];
             L.face_geom[(6 + d) * NF + j] = fb[d];
+            L.face_geom[(GX + d) * NF + j] = src.f->coordinates[3 * fi + d];
+          } else {
+            const size_t base = (size_t)6 * T.face_start + e;
+            L.face_geom[base + (0 + d) * fcp] = fn[d];
+            L.face_geom[base + (3 + d) * fcp] = src.f->coordinates[3 * fi + d];
           }
-          L.face_geom[(GX + d) * NF + j] = src.f->coordinates[3 * fi + d];
         }
         {  // how far (n/|n|, t, b/|n|) is from orthonormal (FAST arithmetic relies on it, Face.C:81-96)
           const double a2 = fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2];
@@ -391,7 +408,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
           L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (1 << 14) | (side << 15));
           L.face_left[j] = c;
           L.face_right[j] = bc_code(src.bc_type);
-          L.face_lr[j] = (uint32_t)lc | ((uint32_t)(0xFFFF - src.bc_type) << 16);
+          L.face_lr[j] = (uint32_t)(shift + lc) | ((uint32_t)(0xFFFF - src.bc_type) << 16);
         } else {
           L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
           const int oth_old = src.f->face_cell_conn[2 * fi + (1 - side)];
@@ -400,15 +417,17 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
           L.face_right[j] = side == 0 ? oth_new : c;
           int oth_local;
           if (cut) {
-            oth_local = T.cell_count + (e - T.cut_start);
+            oth_local = halo_base + (e - T.cut_start);
             L.tile_halo[(size_t)T.halo_start + (e - T.cut_start)] = oth_new;
           } else {
-            oth_local = oth_new - T.cell_start;
+            oth_local = shift + (oth_new - T.cell_start);
             const int os = src.f->cell_flux_index[2 * fi + (1 - side)];
             L.slot_face[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(e | ((1 - side) << 15));
+            L.slot_nbr[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(shift + lc);
           }
-          L.face_lr[j] = side == 0 ? ((uint32_t)lc | ((uint32_t)oth_local << 16))
-                                   : ((uint32_t)oth_local | ((uint32_t)lc << 16));
+          L.slot_nbr[(size_t)s * L.slot_stride + c] = (uint16_t)oth_local;
+          L.face_lr[j] = side == 0 ? ((uint32_t)(shift + lc) | ((uint32_t)oth_local << 16))
+                                   : ((uint32_t)oth_local | ((uint32_t)(shift + lc) << 16));
         }
       }
     }

@@ -29,7 +29,8 @@ struct HostLayout {
   int n_owned = 0, n_ghost = 0;
   int stride = 0;  // SoA component stride of cell arrays (>= n_owned + n_ghost, multiple of 32)
   int tile_dims[3] = {0, 0, 0};
-  int max_tile_cells = 0, max_tile_faces = 0;
+  int max_tile_cells = 0, max_tile_faces = 0;  // max_tile_cells: the requested brick size (upper bound)
+  int max_tile_cells_real = 0;                 // largest tile actually built
   int n_tiles = 0;
   int n_interior_tiles = 0;  // tiles [0, n_interior_tiles) touch no ghost cell
   long n_tile_faces = 0;     // length of the tile-packed face arrays (with per-tile padding)
@@ -45,18 +46,29 @@ struct HostLayout {
   std::vector<uint16_t> slot_face;
   int slot_stride = 0;
 
-  // tile-packed face SoA, length n_tile_faces each: geometry component g of face j at geom[g*n_tile_faces + j]
-  // with_tangents: g = 0-2 normal, 3-5 tangent, 6-8 binormal, 9-11 centroid (STRICT arithmetic);
-  // otherwise     : g = 0-2 normal, 3-5 centroid (FAST arithmetic never reads tangent / binormal)
+  // neighbour map (FAST kernels): slot_nbr[s][cell] = position of the cell across slot s in the tile's staged cell
+  // list (see face_lr), 0xFFFF for a boundary face
+  std::vector<uint16_t> slot_nbr;
+
+  // tile-packed face geometry.
+  // with_tangents (STRICT arithmetic): global SoA, component g of tile face j at geom[g*n_tile_faces + j],
+  //                g = 0-2 normal, 3-5 tangent, 6-8 binormal, 9-11 centroid;
+  // otherwise (FAST arithmetic, never reads tangent / binormal): tile-blocked SoA, so that one contiguous run holds
+  //                everything a tile needs: component g of tile T's face e at geom[6*T.face_start + g*fcp + e] with
+  //                fcp = T.face_count rounded up to 16, g = 0-2 normal, 3-5 centroid
   int geom_components = 12;
   double max_frame_error = 0.0;  // worst deviation of (n^, t, b/|a|) from an orthonormal frame over all faces
   std::vector<double> face_geom;
   std::vector<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
-  // tile-local connectivity: low 16 bits = left cell, high 16 bits = right cell, as indices into the tile's
-  // [own cells | outside cells of its cut faces] list; a boundary face has right = 0xFFFF - ma_bc_type
+  // tile-local connectivity: low 16 bits = left cell, high 16 bits = right cell, as POSITIONS in the tile's staged
+  // cell list: own cell lc sits at (cell_start & 1) + lc (the staging copy starts at the even cell below
+  // cell_start: 16-byte alignment of the bulk copies), the outside cell of cut face e at
+  // halo_base + (e - cut_start) with halo_base = ((cell_start & 1) + cell_count) rounded up to even;
+  // a boundary face has right = 0xFFFF - ma_bc_type
   std::vector<uint32_t> face_lr;
   std::vector<int> tile_halo;  // renumbered id of the outside cell of every cut face, tile after tile
-  int max_tile_local = 0;      // largest (cells + cut faces) of a tile
+  int max_tile_local = 0;      // largest staged cell list of a tile (halo_base + cut faces)
+  int max_tile_halo = 0;       // largest number of cut faces of a tile
 
   // halo lists in renumbered ids, grouped by neighbour rank ascending
   std::vector<int> send_ids, recv_ids;

@@ -97,7 +97,7 @@ struct ma_solver {
   ma::DevMesh dm;
   ma::TileInfoDev *d_tiles = nullptr;
   double *d_xyz = nullptr, *d_vol = nullptr, *d_geom = nullptr;
-  uint16_t *d_slot = nullptr;
+  uint16_t *d_slot = nullptr, *d_slot_nbr = nullptr;
   int *d_fl = nullptr, *d_fr = nullptr, *d_old2new = nullptr, *d_send_ids = nullptr, *d_recv_ids = nullptr;
   uint32_t *d_face_lr = nullptr;
   int *d_tile_halo = nullptr;
@@ -132,14 +132,18 @@ struct Api {
   decltype(&ma_fast::launch_grad_limiter) grad;
   decltype(&ma_fast::launch_flux_rk) flux;
   decltype(&ma_fast::flux_rk_prepare) prepare;
+  decltype(&ma_fast::grad_smem_bytes) grad_smem;
+  decltype(&ma_fast::flux_smem_bytes) flux_smem;
   decltype(&ma_fast::launch_initial_conditions) ic;
   decltype(&ma_fast::launch_primitives) prims;
 };
 Api api_of(bool strict) {
   if (strict)
     return {&ma_strict::launch_grad_limiter, &ma_strict::launch_flux_rk, &ma_strict::flux_rk_prepare,
+            &ma_strict::grad_smem_bytes, &ma_strict::flux_smem_bytes,
             &ma_strict::launch_initial_conditions, &ma_strict::launch_primitives};
   return {&ma_fast::launch_grad_limiter, &ma_fast::launch_flux_rk, &ma_fast::flux_rk_prepare,
+          &ma_fast::grad_smem_bytes, &ma_fast::flux_smem_bytes,
           &ma_fast::launch_initial_conditions, &ma_fast::launch_primitives};
 }
 
@@ -357,7 +361,7 @@ void ma_solver_destroy(ma_solver *S) {
   if (S->st) cudaStreamSynchronize(S->st);
   if (S->cs) cudaStreamSynchronize(S->cs);
   void *ptrs[] = {S->d_tiles, S->d_xyz,  S->d_vol,  S->d_geom, S->d_slot,    S->d_fl,      S->d_fr,   S->d_old2new,
-                  S->d_send_ids, S->d_recv_ids, S->d_face_lr, S->d_tile_halo, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
+                  S->d_send_ids, S->d_recv_ids, S->d_face_lr, S->d_tile_halo, S->d_slot_nbr, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
                   S->d_sendbuf, S->d_recvbuf, S->d_stage};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -389,9 +393,10 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   int rc = check_device(cfg.device);
   if (rc) return rc;
 
-  // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 8x4x4 for the FAST tile kernels, whose
-  // shared-memory face staging (18 doubles per tile face) should leave room for three CTAs per SM
-  const int td_default[2][3] = {{8, 8, 4}, {8, 8, 8}};
+  // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 8x4x4 for the FAST staged kernels, whose
+  // shared-memory footprint (28 doubles per own cell + 6 per face + 11 RK operands) leaves room for three CTAs per SM;
+  // z is the fastest cell index inside a tile, so the long z edge makes the cut-face gathers along x and y contiguous
+  const int td_default[2][3] = {{4, 4, 8}, {8, 8, 8}};
   int td[3];
   for (int d = 0; d < 3; ++d)
     td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : td_default[cfg.arith == MA_ARITH_STRICT ? 1 : 0][d];
@@ -468,6 +473,7 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   MA_TRY(dev_upload(&S->d_geom, L.face_geom, &S->device_bytes));
   std::vector<double>().swap(L.face_geom);
   MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
+  if (!S->strict) MA_TRY(dev_upload(&S->d_slot_nbr, L.slot_nbr, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_fr, L.face_right, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_face_lr, L.face_lr, &S->device_bytes));
@@ -502,13 +508,18 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   m.slot_stride = L.slot_stride;
   m.n_tile_faces = L.n_tile_faces;
   m.flux_smem_stride = (L.max_tile_faces + 15) / 16 * 16 + 1;  // odd stride: conflict-free across components
-  m.local_smem_stride = (L.max_tile_local + 15) / 16 * 16 + 1;
   m.rk_smem_stride = (L.max_tile_cells + 15) / 16 * 16 + 1;
-  {  // experiment knobs (FAST only): MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tile
+  m.max_tile_cells = L.max_tile_cells_real, m.max_tile_faces = L.max_tile_faces;
+  m.max_tile_halo = L.max_tile_halo, m.max_tile_local = L.max_tile_local;
+  {  // FAST: the bulk-copy staged tile kernels when a capacity class holds every tile, else the gather kernels.
+     // Experiment knobs: MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma
     const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
-    m.grad_variant = (gv && !strcmp(gv, "gather")) ? 0 : 1;  // default: shared-memory staged neighbours
-    m.flux_variant = (fv && !strcmp(fv, "tile")) ? 1 : 0;
+    m.tile_class = S->strict ? -1 : ma_fast::pick_tile_class(m.max_tile_cells, m.max_tile_faces, m.max_tile_halo);
+    m.grad_variant = (m.tile_class >= 0 && !(gv && !strcmp(gv, "gather"))) ? 1 : 0;
+    m.flux_variant = (m.tile_class >= 0 && !(fv && !strcmp(fv, "gather"))) ? 1 : 0;
   }
+  m.slot_nbr = S->d_slot_nbr;
+  m.exp_flags = getenv("MINIAERO_EXP") ? atoi(getenv("MINIAERO_EXP")) : 0;
   m.face_lr = S->d_face_lr;
   m.tile_halo = S->d_tile_halo;
   m.tiles = S->d_tiles;
@@ -522,16 +533,16 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   m.inflow[0] = 0.5805, m.inflow[1] = 503.96, m.inflow[2] = 0.0, m.inflow[3] = 0.0, m.inflow[4] = 343750.0;
   {
     const bool strict = S->strict;
-    const size_t fsm = strict ? ma_strict::flux_smem_bytes(m, S->second, S->viscous) : ma_fast::flux_smem_bytes(m, S->second, S->viscous);
-    const size_t gsm = strict ? ma_strict::grad_smem_bytes(m) : ma_fast::grad_smem_bytes(m);
-    const size_t smem = std::max(fsm, gsm);
+    const Api K = api_of(strict);
+    const size_t gather_smem = ((size_t)5 * m.flux_smem_stride + (size_t)11 * m.rk_smem_stride) * sizeof(double);
+    const size_t smem = std::max(std::max(K.flux_smem(m, S->second, S->viscous), K.grad_smem(m, S->second)), gather_smem);
     if (smem > 227 * 1024) {
       ma_solver_destroy(S);
       return ma_set_error(MA_ERR_INVALID, "tile needs more than 227 KB of shared memory; use smaller tile_dims");
     }
-    MA_CU(api_of(strict).prepare((int)smem));
+    MA_CU(K.prepare(m, (int)gather_smem));
     if (cfg.block_threads <= 0 && !strict) {
-      S->flux_threads = 256;
+      S->flux_threads = m.flux_variant == 1 ? ma_fast::tile_class_threads(m.tile_class, 1) : 256;
       S->grad_threads = 128;
     }
   }

@@ -18,7 +18,8 @@ def main():
     opt = ma.Options(problem_type=ptype, lx=geo[0], ly=geo[1], lz=geo[2], angle=30.0 if ptype == 2 else 0.0, nx=nx,
                      ny=ny, nz=nz, ntimesteps=steps, dt=geo[3], second_order_space=second, viscous=visc)
     mesh = ma.Parallel3DMesh.from_options(opt).fillMeshData()
-    s = ma.TimeSolverExplicitRK4(mesh, opt, arith=arith)
+    tile = tuple(int(x) for x in os.environ.get('MINIAERO_TILE', '0,0,0').split(','))
+    s = ma.TimeSolverExplicitRK4(mesh, opt, arith=arith, tile_dims=tile)
     s.initialize()
     s.step(steps)
     t = s.timing()
