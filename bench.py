@@ -200,7 +200,7 @@ def reference_arm(args):
                              "sample": sample, "cpu": cpu_model(), "top_functors": r["top_functors"]},
             "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     return 0
 
 
@@ -317,10 +317,10 @@ def gpu_arm(args):
         with open(tp) as f:
             tj = json.load(f)
         key = "flux_rk_o2" if second else "flux_rk_o1"
-        if key in tj:
+        if key in tj:   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per owned cell
             traffic = tj[key]["dram_bytes_per_cell"] * n_owned
     bpcu = BYTES_PER_CELL_UPDATE_O2 if (second or optd["viscous"]) else BYTES_PER_CELL_UPDATE_O1
-    roofline = {"bound": "hbm", "kernel": "flux_rk_kernel (flux + gather + RK stage update)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "flux_rk_tma_kernel (face fluxes + slot-ordered gather + RK stage update)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": flux_bytes, "launch_ms": flux_ms,
                 "share_of_step": t["flux_seconds"] / t["step_seconds"],
@@ -404,7 +404,7 @@ def gpu_arm(args):
                 "wall_ms_per_step": 1e3 * t["wall_seconds"] / args.steps, "result_finite": finite}
         if also:
             line["also"] = also
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -427,6 +427,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version banner, ...)
+    # goes to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     return reference_arm(args) if args.impl == "reference" else gpu_arm(args)
 
 

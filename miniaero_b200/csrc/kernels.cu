@@ -13,6 +13,8 @@
 //                         phase 2, thread per cell: deterministic slot-ordered gather of the six face
 //                         fluxes (Flux.h:216-227, the reference's -DCELL_FLUX order), residual, and the
 //                         fused RK update (TimeSolverExplicitRK4.h:106-128,355,483).
+#include <algorithm>
+
 #include "kernels.h"
 #include "physics.cuh"
 
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
             mn[k] = fmin(mn[k], fmin(Vn[k], V[k]));  // StencilLimiter.h:139-140,272-273
             mx[k] = fmax(mx[k], fmax(Vn[k], V[k]));
 #else
-            mn[k] = fmin(mn[k], Vn[k]);
-            mx[k] = fmax(mx[k], Vn[k]);
+            mn[k] = dmin(mn[k], Vn[k]);
+            mx[k] = dmax(mx[k], Vn[k]);
 #endif
           }
         }
@@ -487,8 +489,9 @@ MA_DEV void cp_async8s(unsigned dst, const double *gmem_src) {
 
 // Capacity class of a tile: the staged kernels are compiled for a few (cells, faces, cut faces) capacities so
 // that every shared-memory stride is a compile-time constant.
-template <int CELLS, int FACES, int HALO, int GRAD_T, int GRAD_B, int FLUX_T, int FLUX_B>
+template <int CELLS, int FACES, int HALO, int GRAD_T, int GRAD_B, int GRAD_B1, int FLUX_T, int FLUX_B>
 struct TileCap {
+  static constexpr int GRAD_MINB1 = GRAD_B1;  // resident CTAs per SM of the one-tile-per-CTA gradient kernel
   static constexpr int NC = CELLS;                          // own cells
   static constexpr int FC = (FACES + 15) / 16 * 16;         // tile faces (the copy length is rounded up to 16)
   static constexpr int HC = HALO;                           // cut faces == staged outside cells
@@ -497,81 +500,31 @@ struct TileCap {
   static constexpr int SC = CELLS + 8;                      // staged slot map (uint16, 16-byte alignment slack)
   static constexpr int GRAD_THREADS = GRAD_T, GRAD_MINB = GRAD_B, FLUX_THREADS = FLUX_T, FLUX_MINB = FLUX_B;
 };
-using Cap64 = TileCap<64, 240, 96, 64, 8, 96, 6>;      // 4x4x4 bricks
-using Cap128 = TileCap<128, 464, 160, 128, 4, 160, 3>;  // 8x4x4 bricks
-using Cap256 = TileCap<256, 896, 256, 256, 2, 256, 1>;  // 8x8x4 bricks
+using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
+using Cap128 = TileCap<128, 464, 160, 128, 3, 4, 128, 3>;  // 8x4x4 / 4x4x8 bricks (flux: 12 warps per SM, 168 registers, no spills)
+using Cap256 = TileCap<256, 896, 256, 256, 1, 2, 256, 1>;  // 8x8x4 bricks
 
 // ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
-// thread per own cell (blockDim >= cells of the tile); neighbours, face normals and centroids from shared memory
-template <bool SECOND, class CAP>
-__global__ void __launch_bounds__(CAP::GRAD_THREADS, CAP::GRAD_MINB)
-    grad_limiter_tma_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
-                            double *__restrict__ lim, int tile_begin) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NG = SECOND ? 6 : 3;  // normal (+ centroid)
-  constexpr int FC = CAP::FC, LS = CAP::LS;
-  double *sG = reinterpret_cast<double *>(smem_raw);  // [NG][FC]
-  double *sV = sG + NG * FC;                          // [5][LS]
-  const unsigned bar = smem_addr(sV + 5 * LS);
-  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
-  const int tid = threadIdx.x;
-  const int nc = T.cell_count;
-  const int shift = T.cell_start & 1;
-  const int hb = (shift + nc + 1) & ~1;  // doubles per staged own-cell run == first outside-cell position
-  const int nh = T.face_count - T.cut_start;
-  const unsigned fcp = (unsigned)(T.face_count + 15) & ~15u;
-  if (tid == 0) {
-    mbar_init(bar, blockDim.x + 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid < 32) {
-    const unsigned gbytes = fcp * 8u, vbytes = (unsigned)hb * 8u;
-    if (tid == 0) mbar_arrive_expect_tx(bar, NG * gbytes + 5 * vbytes);
-    __syncwarp();
-    if (tid < NG) bulk_g2s(smem_addr(sG + tid * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)tid * fcp, gbytes, bar);
-    else if (tid < NG + 5)
-      bulk_g2s(smem_addr(sV + (tid - NG) * LS), V_ + (size_t)(tid - NG) * m.stride + (T.cell_start - shift), vbytes, bar);
-  }
-  for (int h = tid; h < nh; h += blockDim.x) {
-    const int c = __ldg(m.tile_halo + T.halo_start + h);
-#pragma unroll
-    for (int k = 0; k < 5; ++k) cp_async8s(smem_addr(sV + k * LS + hb + h), V_ + (size_t)k * m.stride + c);
-  }
-  mbar_cp_async_arrive(bar);
-
-  // per-cell operands that only this thread needs: straight to registers, in flight together with the copies
-  const bool active = tid < nc;
-  const int c = T.cell_start + (active ? tid : 0);
-  unsigned sn[6];  // slot_face | slot_nbr << 16
-#pragma unroll
-  for (int s = 0; s < 6; ++s)
-    sn[s] = (unsigned)__ldg(m.slot_face + (size_t)s * m.slot_stride + c) |
-            ((unsigned)__ldg(m.slot_nbr + (size_t)s * m.slot_stride + c) << 16);
-  const double vol = __ldg(m.cell_vol + c);
-  double xc[3] = {0.0, 0.0, 0.0};
-  if (SECOND) {
-#pragma unroll
-    for (int d = 0; d < 3; ++d) xc[d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
-  }
-  mbar_wait(bar, 0);
-  if (!active) return;
-
+// One own cell: neighbours (sV), face normals and centroids (sG) from shared memory; sn[s] = slot_face | slot_nbr << 16
+template <bool SECOND, int FC, int LS>
+MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const double *__restrict__ sV, int pos,
+                              const unsigned (&sn)[6], double vol, const double (&xc)[3], int c, int stride,
+                              double *__restrict__ grad, double *__restrict__ lim) {
   double V[5], g[5][3], mn[5], mx[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
-    V[k] = sV[k * LS + shift + tid];
+    V[k] = sV[k * LS + pos];
     g[k][0] = g[k][1] = g[k][2] = 0;
     mn[k] = mx[k] = V[k];  // min/max over {cell, face neighbours} (StencilLimiter.h:139-140, 272-273)
   }
 #pragma unroll
   for (int s = 0; s < 6; ++s) {
     const int e = (int)(sn[s] & 0x3fffu);
-    const double sgn = (sn[s] & 0x8000u) ? -1.0 : 1.0;
+    const bool right = (sn[s] & 0x8000u) != 0;  // the normal points out of elem1: flip it for elem2
     const unsigned nb = sn[s] >> 16;
     double an[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) an[d] = sgn * sG[d * FC + e];
+    for (int d = 0; d < 3; ++d) an[d] = flip_sign_if(sG[d * FC + e], right);
     if (nb != 0xFFFFu) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
@@ -580,8 +533,8 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, CAP::GRAD_MINB)
 #pragma unroll
         for (int d = 0; d < 3; ++d) g[k][d] = fma(sum, an[d], g[k][d]);
         if (SECOND) {
-          mn[k] = fmin(mn[k], vn);
-          mx[k] = fmax(mx[k], vn);
+          mn[k] = dmin(mn[k], vn);
+          mx[k] = dmax(mx[k], vn);
         }
       }
     } else {
@@ -600,7 +553,7 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, CAP::GRAD_MINB)
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         g[k][d] *= half_rvol;
-        grad[(size_t)(k * 3 + d) * m.stride + c] = g[k][d];
+        grad[(size_t)(k * 3 + d) * stride + c] = g[k][d];
       }
   }
   if (SECOND) {
@@ -623,7 +576,7 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, CAP::GRAD_MINB)
       }
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double dU = disp[0] * g[k][0] + disp[1] * g[k][1] + disp[2] * g[k][2];  // StencilLimiter.h:438-446
+        const double dU = fma(disp[2], g[k][2], fma(disp[1], g[k][1], disp[0] * g[k][0]));  // StencilLimiter.h:438-446
         // VenkatLimiter.h:45-73 with a = |du|, mm = |dumax| or |dumin| by the sign of du and the common factor
         // du cancelled: phi = (mm^2 + eps2 + 2 a mm) / (mm^2 + eps2 + a (2a + mm)); phi -> 1 as a -> 0
         const double aa = fabs(dU);
@@ -634,7 +587,122 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, CAP::GRAD_MINB)
       }
     }
 #pragma unroll
-    for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = quot(pN[k], pD[k]);
+    for (int k = 0; k < 5; ++k) lim[(size_t)k * stride + c] = quot(pN[k], pD[k]);
+  }
+}
+
+// Persistent, double-buffered: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While it computes tile i
+// out of one shared-memory stage, the bulk copies and the outside-cell gathers of tile i+1 land in the other
+// stage, and the tile descriptor / outside-cell ids of tile i+2 are on their way to registers: no load on the
+// arithmetic's critical path after the first tile.  Thread per own cell (blockDim >= cells of a tile).
+template <bool SECOND, class CAP, bool PERSIST>
+__global__ void __launch_bounds__(CAP::GRAD_THREADS, PERSIST ? CAP::GRAD_MINB : CAP::GRAD_MINB1)
+    grad_limiter_tma_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
+                            double *__restrict__ lim, int tile_begin, int ntiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NG = SECOND ? 6 : 3;  // normal (+ centroid)
+  constexpr int FC = CAP::FC, LS = CAP::LS;
+  constexpr int STAGE = NG * FC + 5 * LS;  // doubles per stage: sG[NG][FC], sV[5][LS]
+  constexpr int HPT = (CAP::HC + CAP::GRAD_THREADS - 1) / CAP::GRAD_THREADS;  // outside cells per thread
+  double *sbase = reinterpret_cast<double *>(smem_raw) + 2;  // two mbarriers, then the stages
+  const unsigned bar0 = smem_addr(smem_raw);
+  const int tid = threadIdx.x;
+  const int G = gridDim.x;
+  int t = blockIdx.x;
+  if (t >= ntiles) return;
+  const TileInfoDev *tiles = m.tiles + tile_begin;
+  if (tid == 0) {
+    mbar_init(bar0, blockDim.x + 1);
+    mbar_init(bar0 + 8, blockDim.x + 1);
+    mbar_fence_init();
+  }
+  int ids0[HPT], ids1[HPT];
+  // tile descriptors: current, next, the one after
+  TileInfoDev T0 = tiles[t], T1 = T0, T2 = T0;
+  if (t + G < ntiles) T1 = tiles[t + G];
+  if (t + 2 * G < ntiles) T2 = tiles[t + 2 * G];
+  // outside cells of this thread's cut faces of the CTA's tile number `tile` (-1: none); the address needs only
+  // the tile index, so the loads fly together with the tile descriptor's
+  auto load_ids = [&](int tile, int (&ids)[HPT]) {
+    const int *p = m.tile_halo + (size_t)(tile_begin + tile) * m.halo_stride;
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {
+      const int h = tid + j * CAP::GRAD_THREADS;
+      ids[j] = h < m.halo_stride ? __ldg(p + h) : -1;
+    }
+  };
+  // start every copy of tile T into stage st; ids = outside cells of this thread
+  auto issue = [&](const TileInfoDev &T, int st, const int (&ids)[HPT]) {
+    double *sG = sbase + st * STAGE, *sV = sG + NG * FC;
+    const unsigned bar = bar0 + 8 * st;
+    const int shift = T.cell_start & 1;
+    const int hb = (shift + T.cell_count + 1) & ~1;  // doubles per staged own-cell run == first outside-cell position
+    const unsigned fcp = (unsigned)(T.face_count + 15) & ~15u;
+    if (tid < 32) {
+      const unsigned gbytes = fcp * 8u, vbytes = (unsigned)hb * 8u;
+      if (tid == 0) mbar_arrive_expect_tx(bar, NG * gbytes + 5 * vbytes);
+      __syncwarp();
+      // generic-proxy reads of this stage (ordered before by the CTA barrier) precede the copy engine's writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tid < NG)
+        bulk_g2s(smem_addr(sG + tid * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)tid * fcp, gbytes, bar);
+      else if (tid < NG + 5)
+        bulk_g2s(smem_addr(sV + (tid - NG) * LS), V_ + (size_t)(tid - NG) * m.stride + (T.cell_start - shift), vbytes, bar);
+    }
+#pragma unroll
+    for (int j = 0; j < HPT; ++j) {
+      if (ids[j] >= 0) {
+        const int h = tid + j * CAP::GRAD_THREADS;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) cp_async8s(smem_addr(sV + k * LS + hb + h), V_ + (size_t)k * m.stride + ids[j]);
+      }
+    }
+    mbar_cp_async_arrive(bar);
+  };
+  // per-cell operands that only this thread needs: registers, loaded one tile ahead
+  struct CellRegs {
+    unsigned sn[6];  // slot_face | slot_nbr << 16
+    double vol, xc[3];
+  };
+  auto load_cell = [&](const TileInfoDev &T, CellRegs &r) {
+    const int c = T.cell_start + (tid < T.cell_count ? tid : 0);
+#pragma unroll
+    for (int s = 0; s < 6; ++s)
+      r.sn[s] = (unsigned)__ldg(m.slot_face + (size_t)s * m.slot_stride + c) |
+                ((unsigned)__ldg(m.slot_nbr + (size_t)s * m.slot_stride + c) << 16);
+    r.vol = __ldg(m.cell_vol + c);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) r.xc[d] = SECOND ? __ldg(m.cell_xyz + (size_t)d * m.stride + c) : 0.0;
+  };
+
+  load_ids(t, ids0);
+  if (t + G < ntiles) load_ids(t + G, ids1);
+  __syncthreads();  // barriers initialised
+  issue(T0, 0, ids0);
+  CellRegs cur, nxt;
+  load_cell(T0, cur);
+  nxt = cur;
+  for (int i = 0;; ++i) {
+    const int st = i & 1;
+    const bool has1 = t + G < ntiles, has2 = t + 2 * G < ntiles;
+    TileInfoDev T3 = T2;
+    if (has1) {
+      issue(T1, st ^ 1, ids1);
+      load_cell(T1, nxt);
+      if (has2) load_ids(t + 2 * G, ids1);                 // consumed at the top of the next iteration
+      if (t + 3 * G < ntiles) T3 = tiles[t + 3 * G];       // consumed two iterations from now
+    }
+    mbar_wait(bar0 + 8 * st, (unsigned)(i >> 1) & 1u);
+    if (tid < T0.cell_count) {
+      const double *sG = sbase + st * STAGE, *sV = sG + NG * FC;
+      grad_limiter_cell<SECOND, FC, LS>(sG, sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc, T0.cell_start + tid,
+                                        m.stride, grad, lim);
+    }
+    if (!has1) break;
+    __syncthreads();  // every read of stage st is done before tile i+2 is copied into it
+    T0 = T1, T1 = T2, T2 = T3;
+    cur = nxt;
+    t += G;
   }
 }
 
@@ -658,7 +726,8 @@ struct FluxRec {
 template <bool SECOND, bool VISCOUS, class CAP>
 constexpr size_t flux_tma_smem() {
   using R = FluxRec<SECOND, VISCOUS>;
-  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + 11 * CAP::RC) * 8 + (size_t)CAP::FC * 4 + (size_t)6 * CAP::SC * 2 + 16;
+  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + 11 * CAP::RC) * 8 + (size_t)CAP::FC * 4 +
+         (size_t)6 * CAP::SC * 2 + 16;
 }
 
 // a cell record in shared memory (component stride RC) or in registers
@@ -746,15 +815,19 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   double *sRec = reinterpret_cast<double *>(smem_raw);                   // [NREC][RC]
   double *sG = sRec + NREC * RC;                                         // [NGS][FC]
   double *sRK = sG + R::NGS * FC;                                        // [11][RC]
-  unsigned *sLR = reinterpret_cast<unsigned *>(sRK + 11 * RC);           // [FC]
+  unsigned *sLR = reinterpret_cast<unsigned *>(sRK + 11 * RC);  // [FC]
   unsigned short *sSlot = reinterpret_cast<unsigned short *>(sLR + FC);  // [6][SC]
   const unsigned bar = smem_addr(sSlot + 6 * SC);
-  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   const int tid = threadIdx.x;
+  // outside cell of this thread's cut face (-1: none): its address needs only the tile index, so the load flies
+  // together with the tile descriptor's
+  const int *halo_ids = m.tile_halo + (size_t)(tile_begin + blockIdx.x) * m.halo_stride;
+  const int my_outside = tid < m.halo_stride ? __ldg(halo_ids + tid) : -1;
+  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   const int nc = T.cell_count, nf = T.face_count;
   const int shift = T.cell_start & 1;
   const int hb = (shift + nc + 1) & ~1;  // doubles per staged own-cell run; positions >= hb are outside cells
-  const int nh = (m.exp_flags & 1) ? 0 : nf - T.cut_start;
+  const int nh = nf - T.cut_start;
   const unsigned fcp = (unsigned)(nf + 15) & ~15u;
   const int sshift = T.cell_start & 7;
   if (tid == 0) {
@@ -801,8 +874,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   }
   // the outside-cell record of this thread's cut face: registers, in flight together with the copies
   double orec[NREC];
-  auto gather_outside = [&](int h) {
-    const int c = __ldg(m.tile_halo + T.halo_start + h);
+  auto gather_outside = [&](int c) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) orec[k] = __ldg(a.V + (size_t)k * m.stride + c);
     if (R::GRAD) {
@@ -816,15 +888,14 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
       for (int d = 0; d < 3; ++d) orec[R_X + d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
     }
   };
-  if (tid < nh) gather_outside(tid);
+  if (my_outside >= 0) gather_outside(my_outside);
   mbar_wait(bar, 0);
 
   // ---- phase 1: one flux per tile face.  Work item w: cut face cut_start + w for w < nh, closed / boundary face
   // w - nh otherwise; thread t takes w = t, t + blockDim, ...
-  const int nwork = (m.exp_flags & 2) ? 0 : nf;
   int w = tid;
-  for (; w < nh && w < nwork; w += blockDim.x) {  // cut faces (one per thread unless blockDim < cut faces of the tile)
-    if (w != tid) gather_outside(w);
+  for (; w < nh; w += blockDim.x) {  // cut faces (one per thread unless blockDim < cut faces of the tile)
+    if (w != tid) gather_outside(__ldg(halo_ids + w));
     const int e = T.cut_start + w;
     const unsigned lr = sLR[e];
     const int pl = (int)(lr & 0xffffu), pr = (int)(lr >> 16);
@@ -849,7 +920,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
 #pragma unroll
     for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];  // this thread's own column: geometry is dead
   }
-  for (; w < nwork; w += blockDim.x) {  // closed and boundary faces
+  for (; w < nf; w += blockDim.x) {  // closed and boundary faces
     const int e = w - nh;
     const unsigned lr = sLR[e];
     const int pl = (int)(lr & 0xffffu);
@@ -1059,9 +1130,26 @@ int tile_class_threads(int cls, int which) {
   }
   return 0;
 }
+// MINIAERO_GRAD_PERSIST=1: the gradient kernel as a persistent, double-buffered pipeline (tile i+1 is copied while
+// tile i is computed).  Measured slower than one tile per CTA (0.77 vs 0.73 ms at 8.4 M cells): the kernel is bound
+// by FP64 issue and warp count, not by the copy latency, and the second stage costs one resident CTA per SM.
+static bool grad_persistent() {
+  const char *e = getenv("MINIAERO_GRAD_PERSIST");
+  return e && e[0] == '1';
+}
 template <class CAP>
-static size_t grad_tma_smem(bool second) {
-  return (size_t)((second ? 6 : 3) * CAP::FC + 5 * CAP::LS) * 8 + 16;
+static size_t grad_tma_smem(bool second) {  // one or two stages + two mbarriers
+  return (size_t)(grad_persistent() ? 2 : 1) * ((second ? 6 : 3) * CAP::FC + 5 * CAP::LS) * 8 + 16;
+}
+// grid of a persistent kernel: resident CTAs per SM x SMs of the current device
+static int persistent_ctas(int ctas_per_sm) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms * ctas_per_sm;
 }
 template <class CAP>
 static size_t flux_tma_smem_rt(bool second, bool viscous) {
@@ -1090,10 +1178,18 @@ template <class CAP>
 static cudaError_t launch_grad_tma(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                    int tile_begin, int ntiles, cudaStream_t st) {
   const size_t smem = grad_tma_smem<CAP>(second);
-  if (second)
-    grad_limiter_tma_kernel<true, CAP><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin);
-  else
-    grad_limiter_tma_kernel<false, CAP><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin);
+  if (grad_persistent()) {
+    const int grid = std::min(ntiles, persistent_ctas(CAP::GRAD_MINB));
+    if (second)
+      grad_limiter_tma_kernel<true, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+    else
+      grad_limiter_tma_kernel<false, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+  } else {
+    if (second)
+      grad_limiter_tma_kernel<true, CAP, false><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+    else
+      grad_limiter_tma_kernel<false, CAP, false><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+  }
   return cudaGetLastError();
 }
 template <class CAP>
@@ -1116,8 +1212,10 @@ static cudaError_t prepare_tma() {
 #define MA_SET(K, BYTES)                                                                   \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));  \
   if (e != cudaSuccess) return e;
-  MA_SET((grad_limiter_tma_kernel<true, CAP>), grad_tma_smem<CAP>(true))
-  MA_SET((grad_limiter_tma_kernel<false, CAP>), grad_tma_smem<CAP>(false))
+  MA_SET((grad_limiter_tma_kernel<true, CAP, true>), grad_tma_smem<CAP>(true))
+  MA_SET((grad_limiter_tma_kernel<false, CAP, true>), grad_tma_smem<CAP>(false))
+  MA_SET((grad_limiter_tma_kernel<true, CAP, false>), grad_tma_smem<CAP>(true))
+  MA_SET((grad_limiter_tma_kernel<false, CAP, false>), grad_tma_smem<CAP>(false))
   MA_SET((flux_rk_tma_kernel<true, true, CAP>), (flux_tma_smem<true, true, CAP>()))
   MA_SET((flux_rk_tma_kernel<true, false, CAP>), (flux_tma_smem<true, false, CAP>()))
   MA_SET((flux_rk_tma_kernel<false, true, CAP>), (flux_tma_smem<false, true, CAP>()))

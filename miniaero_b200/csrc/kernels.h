@@ -20,9 +20,9 @@ struct DevMesh {
   int flux_smem_stride;                // per-component stride of the shared-memory face staging (>= faces of a tile)
   int rk_smem_stride;                  // per-component stride of the staged RK operands (>= cells of a tile)
   int grad_variant, flux_variant;      // FAST kernels: 0 = gather kernels, 1 = bulk-copy (TMA) staged tile kernels
-  int exp_flags;                       // experiment switches (MINIAERO_EXP), 0 in production
   int tile_class;                      // capacity class of the staged tile kernels (kernels.cu: TileClass), -1: none fits
   int max_tile_cells, max_tile_faces, max_tile_halo, max_tile_local;
+  int halo_stride;                     // tile_halo entries per tile (tile k's list starts at k * halo_stride, -1 padded)
   const TileInfoDev *tiles;
   const double *cell_xyz;              // [3][stride]
   const double *cell_vol;              // [stride]
@@ -32,7 +32,7 @@ struct DevMesh {
                                        // FAST tile-blocked [tile][6][faces of the tile rounded up to 16]: normal, centroid
   const int *face_left, *face_right;   // [n_tile_faces] renumbered cell ids (STRICT kernels only)
   const uint32_t *face_lr;             // [n_tile_faces] tile-local left | right << 16 (boundary: 0xFFFF - type)
-  const int *tile_halo;                // outside cell of every cut face, tile after tile
+  const int *tile_halo;                // outside cell of every cut face, halo_stride entries per tile
   double inflow[5];                    // TimeSolverExplicitRK4.h:218-223
 };
 

@@ -331,10 +331,14 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.max_tile_faces = max_faces;
   L.max_tile_local = max_local;
   L.max_tile_halo = max_halo;
+  // every tile owns halo_stride entries of tile_halo (unused ones are -1): the list of a tile sits at an address
+  // computable from the tile index alone, so a CTA can fetch it together with — not after — its tile descriptor
+  L.halo_stride = std::max(4, round_up(max_halo, 4));
+  if ((long)n_tiles * L.halo_stride >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 tile halo entries");
   long real = 0;
   for (long k = 0; k < n_tiles; ++k) {
     L.tiles[k].face_start = (int)fstart[k];
-    L.tiles[k].halo_start = (int)hstart[k];
+    L.tiles[k].halo_start = (int)(k * L.halo_stride);
     fstart[k + 1] = fstart[k] + round_up(L.tiles[k].face_count, 16);
     hstart[k + 1] = hstart[k] + (L.tiles[k].face_count - L.tiles[k].cut_start);
     real += L.tiles[k].face_count;
@@ -350,7 +354,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.face_right.assign(NF, 0);
   L.face_lr.assign(NF, 0);
   L.slot_nbr.assign((size_t)6 * L.slot_stride, 0xFFFF);
-  L.tile_halo.assign((size_t)hstart[n_tiles], 0);
+  L.tile_halo.assign((size_t)n_tiles * L.halo_stride, -1);
   const char *fo_env = getenv("MINIAERO_FACE_ORDER");
   const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)

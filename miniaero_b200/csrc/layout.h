@@ -66,9 +66,10 @@ struct HostLayout {
   // halo_base + (e - cut_start) with halo_base = ((cell_start & 1) + cell_count) rounded up to even;
   // a boundary face has right = 0xFFFF - ma_bc_type
   std::vector<uint32_t> face_lr;
-  std::vector<int> tile_halo;  // renumbered id of the outside cell of every cut face, tile after tile
+  std::vector<int> tile_halo;  // renumbered id of the outside cell of every cut face, halo_stride entries per tile
   int max_tile_local = 0;      // largest staged cell list of a tile (halo_base + cut faces)
   int max_tile_halo = 0;       // largest number of cut faces of a tile
+  int halo_stride = 0;         // tile k's outside cells are tile_halo[k * halo_stride ...], padded with -1
 
   // halo lists in renumbered ids, grouped by neighbour rank ascending
   std::vector<int> send_ids, recv_ids;

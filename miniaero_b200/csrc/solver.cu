@@ -511,6 +511,7 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   m.rk_smem_stride = (L.max_tile_cells + 15) / 16 * 16 + 1;
   m.max_tile_cells = L.max_tile_cells_real, m.max_tile_faces = L.max_tile_faces;
   m.max_tile_halo = L.max_tile_halo, m.max_tile_local = L.max_tile_local;
+  m.halo_stride = L.halo_stride;
   {  // FAST: the bulk-copy staged tile kernels when a capacity class holds every tile, else the gather kernels.
      // Experiment knobs: MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma
     const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
@@ -519,7 +520,6 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
     m.flux_variant = (m.tile_class >= 0 && !(fv && !strcmp(fv, "gather"))) ? 1 : 0;
   }
   m.slot_nbr = S->d_slot_nbr;
-  m.exp_flags = getenv("MINIAERO_EXP") ? atoi(getenv("MINIAERO_EXP")) : 0;
   m.face_lr = S->d_face_lr;
   m.tile_halo = S->d_tile_halo;
   m.tiles = S->d_tiles;
