@@ -196,6 +196,25 @@ int ma_solver_set_profiling(ma_solver *s, int enabled);
  * tab separated, `precision` significant digits (the reference uses the ostream default, 6). */
 int ma_write_results(const char *path, const ma_mesh *mesh, const double *solution, int precision);
 
+/* Mantevo YAML report — the reference compiles YAML_Doc / YAML_Element (YAML_Doc.C:27-67, YAML_Element.C:97-104)
+ * but never calls them; the host driver here does.  Same grammar: "Mini-Application Name/Version" header, then
+ * "key: value" lines with two spaces of indentation per level, written to
+ * <dir>/<name>-<version>_<YYYY:MM:DD-HH:MM:SS>.yaml (dir NULL or "" = "."). */
+typedef struct ma_report {
+  const char *app_name;    /* NULL = "miniAero-b200" */
+  const char *app_version; /* NULL = "1.0" */
+  const ma_options *options;
+  int num_ranks;
+  int blocks[3];            /* block decomposition (Parallel3DMesh.C:247-303) */
+  long long global_cells;   /* owned cells summed over ranks */
+  const ma_timing *timing;  /* of the reporting rank */
+  double setup_seconds, run_seconds, total_seconds; /* Main.C "Setup time" / "Device Run time" / "Total elapsed time" */
+  double hbm_peak_gbs;      /* measured HBM bandwidth the roofline fraction refers to; 0 = omit */
+  const char *device_name;  /* NULL = queried from the CUDA runtime */
+} ma_report;
+/* Writes the file and, when path_out is not NULL, its path (truncated to path_len). */
+int ma_write_yaml_report(const ma_report *report, const char *dir, char *path_out, size_t path_len);
+
 /* ---- Device-function probes (unit parity tests of the physics, run on the GPU) ------------------
  * Each evaluates one reference device function for n independent inputs (arrays are host pointers,
  * row-major).  arith is ma_arith. */

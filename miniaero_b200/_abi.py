@@ -55,6 +55,14 @@ class Timing(C.Structure):
                 ("tile_faces_total", C.c_int)]
 
 
+class Report(C.Structure):
+    """ma_report: the fields of the Mantevo YAML run report (host driver)."""
+    _fields_ = [("app_name", C.c_char_p), ("app_version", C.c_char_p), ("options", C.POINTER(Options)),
+                ("num_ranks", C.c_int), ("blocks", C.c_int * 3), ("global_cells", C.c_longlong),
+                ("timing", C.POINTER(Timing)), ("setup_seconds", C.c_double), ("run_seconds", C.c_double),
+                ("total_seconds", C.c_double), ("hbm_peak_gbs", C.c_double), ("device_name", C.c_char_p)]
+
+
 LIB_NAME = "libminiaero_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
@@ -87,6 +95,7 @@ SYMBOLS = {
     "ma_solver_reset_timing": (C.c_int, [C.c_void_p]),
     "ma_solver_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "ma_write_results": (C.c_int, [C.c_char_p, C.POINTER(Mesh), C.c_void_p, C.c_int]),
+    "ma_write_yaml_report": (C.c_int, [C.POINTER(Report), C.c_char_p, C.c_char_p, C.c_size_t]),
     "ma_probe_roe_flux": (C.c_int, [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int]),
     "ma_probe_viscous_flux": (C.c_int, [C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_int]),
     "ma_probe_primitives": (C.c_int, [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_int]),

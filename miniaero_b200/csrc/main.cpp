@@ -1,0 +1,171 @@
+// Host driver: the reference's Main.C shape (Main.C:53-152) on top of the C ABI.
+//
+//   miniaero [--input FILE] [--arith fast|strict] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]
+//
+// reads ./miniaero.inp (Options.h:86), generates this rank's block of the hex mesh on the host, hands it to the
+// solver (the drop-in for TimeSolverExplicitRK4 at Main.C:139-141), optionally writes results.<rank>
+// (TimeSolverExplicitRK4.h:514-538), and finishes with the Mantevo YAML report.
+//
+// Ranks: one process per GPU, rank / size taken from RANK / WORLD_SIZE (or OMPI_COMM_WORLD_* / PMI_*), device from
+// LOCAL_RANK.  The NCCL unique id travels through a file (MINIAERO_RENDEZVOUS, default
+// /tmp/miniaero_rdv.<MASTER_PORT or 0>): rank 0 writes it, the others poll — the only bootstrap the run needs,
+// standing in for MPI_Init (Main.C:61-63).
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "miniaero_b200.h"
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+double seconds_since(Clock::time_point t0) { return std::chrono::duration<double>(Clock::now() - t0).count(); }
+
+int env_int(std::initializer_list<const char *> names, int fallback) {
+  for (const char *n : names)
+    if (const char *v = getenv(n)) return atoi(v);
+  return fallback;
+}
+
+[[noreturn]] void die(const char *what) {
+  fprintf(stderr, "miniaero: %s: %s\n", what, ma_last_error());
+  exit(1);
+}
+
+// rank 0 publishes the NCCL id in a file, the other ranks wait for it
+bool exchange_id(int rank, unsigned char id[MA_COMM_ID_BYTES]) {
+  std::string path;
+  if (const char *p = getenv("MINIAERO_RENDEZVOUS")) {
+    path = p;
+  } else {
+    const char *port = getenv("MASTER_PORT");
+    path = std::string("/tmp/miniaero_rdv.") + (port ? port : "0");
+  }
+  if (rank == 0) {
+    if (ma_comm_get_unique_id(id)) return false;
+    const std::string tmp = path + ".tmp";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = fwrite(id, 1, MA_COMM_ID_BYTES, f) == MA_COMM_ID_BYTES;
+    fclose(f);
+    return ok && rename(tmp.c_str(), path.c_str()) == 0;
+  }
+  for (int tries = 0; tries < 6000; ++tries) {  // up to 10 minutes: rank 0 may still be generating its mesh
+    if (FILE *f = fopen(path.c_str(), "rb")) {
+      const size_t n = fread(id, 1, MA_COMM_ID_BYTES, f);
+      fclose(f);
+      if (n == MA_COMM_ID_BYTES) return true;
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+  }
+  return false;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  const auto t_start = Clock::now();
+  std::string input = "miniaero.inp", yaml_dir = ".";
+  int arith = MA_ARITH_FAST, precision = 0, tile[3] = {0, 0, 0};
+  bool yaml = true;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&]() -> const char * {
+      if (i + 1 >= argc) {
+        fprintf(stderr, "miniaero: %s needs a value\n", a.c_str());
+        exit(2);
+      }
+      return argv[++i];
+    };
+    if (a == "--input") input = next();
+    else if (a == "--arith") arith = !strcmp(next(), "strict") ? MA_ARITH_STRICT : MA_ARITH_FAST;
+    else if (a == "--tile") sscanf(next(), "%d,%d,%d", &tile[0], &tile[1], &tile[2]);
+    else if (a == "--precision") precision = atoi(next());
+    else if (a == "--yaml") yaml_dir = next();
+    else if (a == "--no-yaml") yaml = false;
+    else {
+      fprintf(stderr, "usage: miniaero [--input FILE] [--arith fast|strict] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]\n");
+      return a == "--help" || a == "-h" ? 0 : 2;
+    }
+  }
+  const int num_procs = env_int({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE"}, 1);
+  const int my_id = env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK"}, 0);
+  const int device = env_int({"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
+
+  ma_options opt;
+  if (ma_options_read(input.c_str(), &opt)) die("reading the options file");  // Main.C:73-74
+
+  // ---- setup: mesh on the host (Main.C:96-129)
+  const auto t_setup = Clock::now();
+  ma_mesh_storage *mesh = nullptr;
+  if (ma_mesh_generate(&opt, my_id, num_procs, &mesh)) die("mesh generation");
+  int nproc[3], block[3], nlocal[3], offset[3];
+  ma_mesh_decomposition(mesh, nproc, block, nlocal, offset);
+  const double setup_s = seconds_since(t_setup);
+  if (my_id == 0) fprintf(stdout, "\n ... Setup time: %8.2f seconds ...\n", setup_s);
+
+  // ---- run on the device (Main.C:131-150)
+  const auto t_run = Clock::now();
+  ma_comm *comm = nullptr;
+  if (num_procs > 1) {
+    unsigned char id[MA_COMM_ID_BYTES];
+    if (!exchange_id(my_id, id)) {
+      fprintf(stderr, "miniaero: rank %d could not obtain the NCCL id (%s)\n", my_id, ma_last_error());
+      return 1;
+    }
+    if (ma_comm_create(id, num_procs, my_id, device, &comm)) die("communicator");
+  }
+  ma_solver_config cfg;
+  ma_solver_config_default(&cfg);
+  cfg.device = device;
+  cfg.arith = arith;
+  cfg.comm = comm;
+  for (int d = 0; d < 3; ++d) cfg.tile_dims[d] = tile[d];
+  ma_solver *solver = nullptr;
+  if (ma_solver_create(ma_mesh_view(mesh), &opt, &cfg, &solver)) die("solver");
+  if (ma_solver_solve(solver)) die("Solve");  // prints the progress lines and "Device Run time"
+  ma_timing tm;
+  ma_solver_get_timing(solver, &tm);
+  if (my_id == 0)
+    fprintf(stdout, " ... %lld cells x %lld steps: %.4e cell-updates/s on this rank (device time %.3f s) ...\n",
+            (long long)ma_mesh_view(mesh)->num_owned_cells, tm.steps,
+            tm.step_seconds > 0 ? (double)tm.cell_updates / tm.step_seconds : 0.0, tm.step_seconds);
+
+  if (opt.output_results) {  // TimeSolverExplicitRK4.h:514-538
+    const ma_mesh *mv = ma_mesh_view(mesh);
+    std::vector<double> sol((size_t)mv->num_owned_cells * 5);
+    if (ma_solver_get_solution(solver, sol.data())) die("reading the solution back");
+    const std::string name = "results." + std::to_string(my_id);
+    if (ma_write_results(name.c_str(), mv, sol.data(), precision)) die("writing results");
+  }
+  const double run_s = seconds_since(t_run);
+  const double total_s = seconds_since(t_start);
+
+  if (yaml && my_id == 0) {
+    ma_report rep;
+    memset(&rep, 0, sizeof(rep));
+    rep.options = &opt;
+    rep.num_ranks = num_procs;
+    for (int d = 0; d < 3; ++d) rep.blocks[d] = nproc[d];
+    rep.global_cells = (long long)opt.nx * opt.ny * opt.nz;
+    rep.timing = &tm;
+    rep.setup_seconds = setup_s, rep.run_seconds = run_s, rep.total_seconds = total_s;
+    if (const char *pk = getenv("MINIAERO_HBM_PEAK_GBS")) rep.hbm_peak_gbs = atof(pk);
+    char path[512];
+    if (ma_write_yaml_report(&rep, yaml_dir.c_str(), path, sizeof(path)))
+      fprintf(stderr, "miniaero: YAML report not written: %s\n", ma_last_error());
+    else
+      fprintf(stdout, " ... report: %s ...\n", path);
+  }
+  ma_solver_destroy(solver);
+  if (comm) ma_comm_destroy(comm);
+  ma_mesh_free(mesh);
+  if (my_id == 0) fprintf(stdout, "\n ... Total elapsed time: %8.2f seconds ...\n", seconds_since(t_start));  // Main.C:90-92
+  return 0;
+}
