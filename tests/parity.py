@@ -37,6 +37,35 @@ def field_errors(test, ref):
     return float(linf), float(l2)
 
 
+def field_error_parts(test, ref):
+    """The pieces of field_errors for ONE block of a partitioned field: per-field max |error|, sum of squared
+    errors, Linf scale and squared L2 scale (rho, momentum vector x3, rho*E).  combine_parts() turns the blocks'
+    pieces into the norms of the global field."""
+    test = np.asarray(test, dtype=np.float64).reshape(-1, 5)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1, 5)
+    assert test.shape == ref.shape
+    d = test - ref
+    mom2 = (ref[:, 1:4] ** 2).sum(axis=1)
+    linf_scale = [float(np.abs(ref[:, 0]).max()), float(np.sqrt(mom2.max())), float(np.abs(ref[:, 4]).max())]
+    l2_scale2 = [float((ref[:, 0] ** 2).sum()), float(mom2.sum()), float((ref[:, 4] ** 2).sum())]
+    return {"err_max": np.abs(d).max(axis=0).tolist(), "err_sq": (d ** 2).sum(axis=0).tolist(),
+            "linf_scale": linf_scale, "l2_scale2": l2_scale2}
+
+
+def combine_parts(parts):
+    """(linf, l2) of the global field from the per-block pieces: a block is part of ONE field, so its errors are
+    measured on that field's scale — a block the wave has not reached yet (momentum ~1e-7 of the global maximum)
+    has no momentum scale of its own, exactly like the zero components of field_errors."""
+    group = [0, 1, 1, 1, 2]
+    linf_scale = [max(p["linf_scale"][g] for p in parts) for g in range(3)]
+    l2_scale = [np.sqrt(sum(p["l2_scale2"][g] for p in parts)) for g in range(3)]
+    linf_scale = [s if s > 0 else 1.0 for s in linf_scale]
+    l2_scale = [s if s > 0 else 1.0 for s in l2_scale]
+    linf = max(max(p["err_max"][k] for p in parts) / linf_scale[group[k]] for k in range(5))
+    l2 = max(np.sqrt(sum(p["err_sq"][k] for p in parts)) / l2_scale[group[k]] for k in range(5))
+    return float(linf), float(l2)
+
+
 def max_ulp(test, ref):
     """Largest distance in units in the last place between two float64 arrays (0 = bit identical,
     treating +0 and -0 as equal)."""

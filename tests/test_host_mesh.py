@@ -130,3 +130,19 @@ def test_block_meshes_match_the_reference_mpi_build(lib, name, nranks):
         assert o["results"].shape[0] == n
         assert parity.max_ulp(mesh.cell_coordinates, d["cell_coordinates"]) == 0, r
         assert parity.max_ulp(mesh.cell_volumes[:n], d["cell_volumes"][:n]) == 0, r
+
+
+def test_partitioned_norms_equal_the_global_field_norms():
+    """parity.combine_parts over the blocks of a partitioned field == parity.field_errors of the whole field; a block
+    whose momentum is ~0 (the wave has not arrived) is measured on the global momentum scale, not its own."""
+    import parity
+    rng = np.random.default_rng(7)
+    ref = rng.normal(size=(96, 5))
+    ref[:, 4] += 1e5
+    ref[:32, 1:4] *= 1e-9          # a block that is still (almost) at rest
+    test = ref + 1e-13 * rng.normal(size=ref.shape)
+    whole = parity.field_errors(test, ref)
+    parts = [parity.field_error_parts(test[a:b], ref[a:b]) for a, b in ((0, 32), (32, 64), (64, 96))]
+    combined = parity.combine_parts(parts)
+    assert np.allclose(whole, combined, rtol=1e-12)
+    assert parity.field_errors(test[:32], ref[:32])[0] > 1e3 * combined[0]   # the per-block norm would cry wolf
