@@ -509,6 +509,8 @@ struct TileCap {
   static constexpr int RC = CELLS + 2;                      // staged RK operands
   static constexpr int SC = CELLS + 8;                      // staged slot map (uint16, 16-byte alignment slack)
   static constexpr int GRAD_THREADS = GRAD_T, GRAD_MINB = GRAD_B, FLUX_THREADS = FLUX_T, FLUX_MINB = FLUX_B;
+  // cut faces beyond one per flux thread: their outside-cell records are staged in shared memory
+  static constexpr int XC = HALO > FLUX_T ? (HALO - FLUX_T + 1) / 2 * 2 : 0;
 };
 using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
 using Cap128 = TileCap<128, 464, 160, 128, 3, 4, 128, 3>;  // 8x4x4 / 4x4x8 bricks (flux: 12 warps per SM, 168 registers, no spills)
@@ -736,7 +738,7 @@ struct FluxRec {
 template <bool SECOND, bool VISCOUS, class CAP>
 constexpr size_t flux_tma_smem() {
   using R = FluxRec<SECOND, VISCOUS>;
-  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + 11 * CAP::RC) * 8 + (size_t)CAP::FC * 4 +
+  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + 11 * CAP::RC + R::NREC * CAP::XC) * 8 + (size_t)CAP::FC * 4 +
          (size_t)6 * CAP::SC * 2 + 16;
 }
 
@@ -818,14 +820,16 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     flux_rk_tma_kernel(const DevMesh m, const StageArgs a, int tile_begin) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using R = FluxRec<SECOND, VISCOUS>;
-  constexpr int FC = CAP::FC, RC = CAP::RC, SC = CAP::SC;
+  constexpr int FC = CAP::FC, RC = CAP::RC, SC = CAP::SC, XC = CAP::XC;
   constexpr int R_G = R::R_G, R_L = R::R_L, R_X = R::R_X, NREC = R::NREC, NGEOM = R::NGEOM;
   using SRec = SmemRecord<SECOND, VISCOUS, RC>;
+  using XRec = SmemRecord<SECOND, VISCOUS, (XC ? XC : 1)>;
   using RRec = RegRecord<SECOND, VISCOUS>;
   double *sRec = reinterpret_cast<double *>(smem_raw);                   // [NREC][RC]
   double *sG = sRec + NREC * RC;                                         // [NGS][FC]
   double *sRK = sG + R::NGS * FC;                                        // [11][RC]
-  unsigned *sLR = reinterpret_cast<unsigned *>(sRK + 11 * RC);  // [FC]
+  double *sOut = sRK + 11 * RC;                                          // [NREC][XC] outside cells of cut faces >= blockDim
+  unsigned *sLR = reinterpret_cast<unsigned *>(sOut + NREC * XC);        // [FC]
   unsigned short *sSlot = reinterpret_cast<unsigned short *>(sLR + FC);  // [6][SC]
   const unsigned bar = smem_addr(sSlot + 6 * SC);
   const int tid = threadIdx.x;
@@ -841,8 +845,11 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   const int nh = nf - T.cut_start;
   const unsigned fcp = (unsigned)(nf + 15) & ~15u;
   const int sshift = T.cell_start & 7;
+  // outside cell of this thread's second cut face (tiles with more cut faces than the CTA has threads)
+  const int my_outside2 =
+      (XC > 0 && tid < XC && CAP::FLUX_THREADS + tid < m.halo_stride) ? __ldg(halo_ids + CAP::FLUX_THREADS + tid) : -1;
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, XC > 0 ? blockDim.x + 1 : 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -899,15 +906,32 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
       for (int d = 0; d < 3; ++d) orec[R_X + d] = __ldg(m.cell_xyz + (size_t)d * m.stride + c);
     }
   };
+  if (XC > 0) {  // 8-byte asynchronous gathers of the second outside record into shared memory, on the same barrier
+    if (my_outside2 >= 0) {
+      const unsigned dst = smem_addr(sOut + tid);
+      const int c = my_outside2;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) cp_async8s(dst + (unsigned)(k * XC) * 8u, a.V + (size_t)k * m.stride + c);
+      if (R::GRAD) {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) cp_async8s(dst + (unsigned)((R_G + k) * XC) * 8u, a.grad + (size_t)k * m.stride + c);
+      }
+      if (SECOND) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) cp_async8s(dst + (unsigned)((R_L + k) * XC) * 8u, a.lim + (size_t)k * m.stride + c);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) cp_async8s(dst + (unsigned)((R_X + d) * XC) * 8u, m.cell_xyz + (size_t)d * m.stride + c);
+      }
+    }
+    mbar_cp_async_arrive(bar);
+  }
   if (my_outside >= 0) gather_outside(my_outside);
   mbar_wait(bar, 0);
 
   // ---- phase 1: one flux per tile face.  Work item w: cut face cut_start + w for w < nh, closed / boundary face
   // w - nh otherwise; thread t takes w = t, t + blockDim, ...
-  int w = tid;
-  for (; w < nh; w += blockDim.x) {  // cut faces (one per thread unless blockDim < cut faces of the tile)
-    if (w != tid) gather_outside(__ldg(halo_ids + w));
-    const int e = T.cut_start + w;
+  // a cut face: `outside` is the record of the cell on the other side of the tile boundary
+  auto cut_face = [&](int e, auto outside) {
     const unsigned lr = sLR[e];
     const int pl = (int)(lr & 0xffffu), pr = (int)(lr >> 16);
     FaceGeom G;
@@ -918,7 +942,6 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
       xf[d] = SECOND ? sG[(3 + d) * FC + e] : 0.0;
     }
     double Vl[5], Vr[5], gs[5][3], flux[5];
-    const RRec outside{orec};
     // the outside record first: its registers are free before the own cell's record is read
     if (pr >= hb) {  // outside cell on the right
       face_side<SECOND, VISCOUS, true>(outside, xf, Vr, gs);
@@ -930,6 +953,19 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     interior_flux<VISCOUS>(Vl, Vr, gs, G, flux);
 #pragma unroll
     for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];  // this thread's own column: geometry is dead
+  };
+  int w = tid;
+  if (w < nh) {  // first cut face of this thread: outside record in registers
+    cut_face(T.cut_start + w, RRec{orec});
+    w += blockDim.x;
+  }
+  for (; w < nh; w += blockDim.x) {  // further cut faces: outside record staged in shared memory, else gathered now
+    if (XC > 0 && blockDim.x == CAP::FLUX_THREADS && w - (int)blockDim.x < XC) {
+      cut_face(T.cut_start + w, XRec{sOut + (w - (int)blockDim.x)});
+    } else {
+      gather_outside(__ldg(halo_ids + w));
+      cut_face(T.cut_start + w, RRec{orec});
+    }
   }
   for (; w < nf; w += blockDim.x) {  // closed and boundary faces
     const int e = w - nh;
