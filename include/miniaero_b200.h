@@ -166,6 +166,14 @@ int ma_solver_synchronize(ma_solver *s);
  * what Solve() copies back as "solution_n" (TimeSolverExplicitRK4.h:516).  `host` may be pinned. */
 int ma_solver_get_solution(ma_solver *s, double *host);
 int ma_solver_set_solution(ma_solver *s, const double *host);
+/* Asynchronous ensemble member: upload `state_in` ([num_owned_cells][5], caller's cell order), advance `nsteps` RK4
+ * steps from it, download the new state into `state_out`.  Returns once the work is queued; `state_in` must stay
+ * untouched and `state_out` is valid only after ma_solver_synchronize().  Consecutive submissions are pipelined
+ * over three streams (upload of member i+1 and download of member i-1 overlap the stepping of member i), which
+ * needs page-locked host buffers to be effective.  The members are independent: each starts from its own
+ * `state_in`, as successive Solve() calls of the reference on different initial states would
+ * (TimeSolverExplicitRK4.h:207-539 with the state of :324-338 replaced by the caller's). */
+int ma_solver_submit(ma_solver *s, const double *state_in, double *state_out, int nsteps);
 
 /* Intermediate fields of the most recent RK stage, caller's cell order (parity checks):
  *   MA_FIELD_GRADIENT [num_owned_cells][5][3]  GreenGauss.h:228-270

@@ -245,6 +245,17 @@ class TimeSolverExplicitRK4:
         assert U.size == self.num_owned_cells * 5
         _abi.check(self._lib.ma_solver_set_solution(self._handle, U.ctypes.data))
 
+    def submit(self, state_in, state_out, nsteps=1):
+        """Queue one ensemble member: upload `state_in`, advance `nsteps` RK4 steps, download into `state_out`
+        (numpy arrays or raw host pointers; pinned memory lets the copies overlap the stepping of the neighbouring
+        members).  Returns immediately; call synchronize() before reading `state_out`."""
+        def ptr(a):
+            if isinstance(a, int):
+                return a
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.num_owned_cells * 5
+            return a.ctypes.data
+        _abi.check(self._lib.ma_solver_submit(self._handle, ptr(state_in), ptr(state_out), nsteps))
+
     def field(self, which):
         shape = {FIELD_GRADIENT: (self.num_owned_cells, 5, 3), FIELD_LIMITER: (self.num_owned_cells, 5),
                  FIELD_STAGE_PRIMITIVES: (self.num_owned_cells, 5)}[which]

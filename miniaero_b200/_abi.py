@@ -65,6 +65,9 @@ class Report(C.Structure):
 
 LIB_NAME = "libminiaero_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# developer knob (tools/build_variants.py): load an experiment build of the same library instead
+if os.environ.get("MINIAERO_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["MINIAERO_B200_LIB"])
 
 # every symbol include/miniaero_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -90,6 +93,7 @@ SYMBOLS = {
     "ma_solver_synchronize": (C.c_int, [C.c_void_p]),
     "ma_solver_get_solution": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ma_solver_set_solution": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ma_solver_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "ma_solver_get_field": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ma_solver_get_timing": (C.c_int, [C.c_void_p, C.POINTER(Timing)]),
     "ma_solver_reset_timing": (C.c_int, [C.c_void_p]),

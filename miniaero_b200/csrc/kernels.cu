@@ -483,11 +483,20 @@ MA_DEV void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+MA_DEV void bulk_prefetch_l2(const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+#ifndef MA_HEADER_AHEAD
+#define MA_HEADER_AHEAD 512
+#endif
+#ifndef MA_FLUX_PREFETCH_MIN_BYTES
+#define MA_FLUX_PREFETCH_MIN_BYTES 0   // prefetch-ahead only runs of at least this many bytes
+#endif
 MA_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // The tile descriptor and outside-cell list of the tile a CTA `ahead` positions later will work on: pulled into L2
 // now, so that CTA's first two loads are L2 hits instead of DRAM round trips.
 MA_DEV void prefetch_tile_header(const DevMesh &m, int tile, int ntiles_end, int tid) {
-  constexpr int ahead = 512;  // about the number of CTAs resident on the device
+  constexpr int ahead = MA_HEADER_AHEAD;  // about the number of CTAs resident on the device
   const int nxt = tile + ahead;
   if (nxt >= ntiles_end) return;
   if (tid == 0) prefetch_l2(m.tiles + nxt);
@@ -497,6 +506,34 @@ MA_DEV void cp_async8s(unsigned dst, const double *gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
 }
 
+// Build-time knobs of the staged flux kernel (defaults = the measured best, profiles/r01e_variants.md;
+// tools/build_variants.py sweeps them):
+//   MA_C128_FT / MA_C128_FB   threads per CTA / resident CTAs per SM of the 128-cell tile class
+//   MA_FLUX_RK_STAGED         1: volume, Un and the RK accumulator of the own cells arrive by bulk copy;
+//                             0: phase 2 reads them from global memory (L2-prefetched at CTA start) — 11 KB less
+//                                shared memory per CTA, which is what a fourth resident CTA needs
+//   MA_FLUX_XC                1: the outside record of a thread's second cut face is staged in shared memory
+//   MA_FLUX_PREFETCH_AHEAD    > 0: each CTA bulk-prefetches into L2 the operand runs of the tile that many CTAs ahead
+#ifndef MA_C128_FT
+#define MA_C128_FT 128
+#endif
+#ifndef MA_C128_FB
+#define MA_C128_FB 4
+#endif
+#ifndef MA_FLUX_RK_STAGED
+#define MA_FLUX_RK_STAGED 0
+#endif
+#ifndef MA_FLUX_XC
+#define MA_FLUX_XC 0
+#endif
+#ifndef MA_FLUX_PREFETCH_AHEAD
+#define MA_FLUX_PREFETCH_AHEAD 0
+#endif
+// timing experiments only (wrong results): 1 = copies and gathers but no face arithmetic, 2 = face arithmetic on
+// whatever shared memory holds (only the connectivity is copied)
+#ifndef MA_FLUX_EXPERIMENT
+#define MA_FLUX_EXPERIMENT 0
+#endif
 // Capacity class of a tile: the staged kernels are compiled for a few (cells, faces, cut faces) capacities so
 // that every shared-memory stride is a compile-time constant.
 template <int CELLS, int FACES, int HALO, int GRAD_T, int GRAD_B, int GRAD_B1, int FLUX_T, int FLUX_B>
@@ -510,10 +547,14 @@ struct TileCap {
   static constexpr int SC = CELLS + 8;                      // staged slot map (uint16, 16-byte alignment slack)
   static constexpr int GRAD_THREADS = GRAD_T, GRAD_MINB = GRAD_B, FLUX_THREADS = FLUX_T, FLUX_MINB = FLUX_B;
   // cut faces beyond one per flux thread: their outside-cell records are staged in shared memory
-  static constexpr int XC = HALO > FLUX_T ? (HALO - FLUX_T + 1) / 2 * 2 : 0;
+  static constexpr int XC = (MA_FLUX_XC && HALO > FLUX_T) ? (HALO - FLUX_T + 1) / 2 * 2 : 0;
+  static constexpr bool RK_STAGED = MA_FLUX_RK_STAGED != 0;
 };
 using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
-using Cap128 = TileCap<128, 464, 160, 128, 3, 4, 128, 3>;  // 8x4x4 / 4x4x8 bricks (flux: 12 warps per SM, 168 registers, no spills)
+#ifndef MA_C128_GB1
+#define MA_C128_GB1 4
+#endif
+using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 8x4x4 / 4x4x8 bricks (flux: 12 warps per SM, 168 registers, no spills)
 using Cap256 = TileCap<256, 896, 256, 256, 1, 2, 256, 1>;  // 8x8x4 bricks
 
 // ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
@@ -738,7 +779,7 @@ struct FluxRec {
 template <bool SECOND, bool VISCOUS, class CAP>
 constexpr size_t flux_tma_smem() {
   using R = FluxRec<SECOND, VISCOUS>;
-  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + 11 * CAP::RC + R::NREC * CAP::XC) * 8 + (size_t)CAP::FC * 4 +
+  return (size_t)(R::NREC * CAP::RC + R::NGS * CAP::FC + (CAP::RK_STAGED ? 11 : 0) * CAP::RC + R::NREC * CAP::XC) * 8 + (size_t)CAP::FC * 4 +
          (size_t)6 * CAP::SC * 2 + 16;
 }
 
@@ -828,7 +869,8 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   double *sRec = reinterpret_cast<double *>(smem_raw);                   // [NREC][RC]
   double *sG = sRec + NREC * RC;                                         // [NGS][FC]
   double *sRK = sG + R::NGS * FC;                                        // [11][RC]
-  double *sOut = sRK + 11 * RC;                                          // [NREC][XC] outside cells of cut faces >= blockDim
+  constexpr bool RKS = CAP::RK_STAGED;
+  double *sOut = sRK + (RKS ? 11 : 0) * RC;                              // [NREC][XC] outside cells of cut faces >= blockDim
   unsigned *sLR = reinterpret_cast<unsigned *>(sOut + NREC * XC);        // [FC]
   unsigned short *sSlot = reinterpret_cast<unsigned short *>(sLR + FC);  // [6][SC]
   const unsigned bar = smem_addr(sSlot + 6 * SC);
@@ -846,8 +888,11 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   const unsigned fcp = (unsigned)(nf + 15) & ~15u;
   const int sshift = T.cell_start & 7;
   // outside cell of this thread's second cut face (tiles with more cut faces than the CTA has threads)
+  // (staged in shared memory when XC > 0; otherwise only its lines are pulled into L2 now and the record is gathered
+  // when the thread gets to that face)
+  constexpr int CUT2 = CAP::HC > CAP::FLUX_THREADS ? CAP::HC - CAP::FLUX_THREADS : 0;
   const int my_outside2 =
-      (XC > 0 && tid < XC && CAP::FLUX_THREADS + tid < m.halo_stride) ? __ldg(halo_ids + CAP::FLUX_THREADS + tid) : -1;
+      (CUT2 > 0 && tid < CUT2 && CAP::FLUX_THREADS + tid < m.halo_stride) ? __ldg(halo_ids + CAP::FLUX_THREADS + tid) : -1;
   if (tid == 0) {
     mbar_init(bar, XC > 0 ? blockDim.x + 1 : 1);
     mbar_fence_init();
@@ -855,13 +900,15 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   __syncthreads();
 
   // ---- copy phase
-  if (tid < 32) {
-    const unsigned vbytes = (unsigned)hb * 8u, gbytes = fcp * 8u, lbytes = fcp * 4u;
-    const unsigned sbytes = (unsigned)((sshift + nc + 7) & ~7) * 2u;
-    const int nrk = 1 + (a.kind != 2 ? 5 : 0) + (a.kind != 0 ? 5 : 0);
-    if (tid == 0) mbar_arrive_expect_tx(bar, (NREC + nrk) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes);
-    __syncwarp();
-    const size_t c0 = (size_t)(T.cell_start - shift);
+  // every contiguous operand run of tile TT: emit(shared-memory destination, global source, bytes)
+  auto for_each_run = [&](const TileInfoDev &TT, auto &&emit) {
+    const int sh = TT.cell_start & 1;
+    const int hbb = (sh + TT.cell_count + 1) & ~1;
+    const unsigned fcq = (unsigned)(TT.face_count + 15) & ~15u;
+    const int ssh = TT.cell_start & 7;
+    const unsigned vbytes = (unsigned)hbb * 8u, gbytes = fcq * 8u, lbytes = fcq * 4u;
+    const unsigned sbytes = (unsigned)((ssh + TT.cell_count + 7) & ~7) * 2u;
+    const size_t c0 = (size_t)(TT.cell_start - sh);
     constexpr int NCOPY = NREC + 11 + NGEOM + 1 + 6;
     for (int i = tid; i < NCOPY; i += 32) {
       if (i < NREC) {
@@ -869,26 +916,49 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
                              : i < R_L ? a.grad + (size_t)(i - R_G) * m.stride
                              : i < R_X ? a.lim + (size_t)(i - R_L) * m.stride
                                        : m.cell_xyz + (size_t)(i - R_X) * m.stride;
-        bulk_g2s(smem_addr(sRec + i * RC), base + c0, vbytes, bar);
+        emit(smem_addr(sRec + i * RC), base + c0, vbytes, true);
       } else if (i < NREC + 11) {
         const int j = i - NREC;
-        if (j == 0)
-          bulk_g2s(smem_addr(sRK), m.cell_vol + c0, vbytes, bar);
-        else if (j < 6) {
-          if (a.kind != 2) bulk_g2s(smem_addr(sRK + j * RC), a.Un + (size_t)(j - 1) * m.stride + c0, vbytes, bar);
-        } else {
-          if (a.kind != 0) bulk_g2s(smem_addr(sRK + j * RC), a.Acc + (size_t)(j - 6) * m.stride + c0, vbytes, bar);
-        }
+        const double *base = j == 0 ? m.cell_vol : j < 6 ? a.Un + (size_t)(j - 1) * m.stride : a.Acc + (size_t)(j - 6) * m.stride;
+        if (j == 0 || (j < 6 ? a.kind != 2 : a.kind != 0)) emit(smem_addr(sRK + j * RC), base + c0, vbytes, RKS);
       } else if (i < NREC + 11 + NGEOM) {
         const int gi = i - NREC - 11;
-        bulk_g2s(smem_addr(sG + gi * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)gi * fcp, gbytes, bar);
+        emit(smem_addr(sG + gi * FC), m.face_geom + (size_t)6 * TT.face_start + (size_t)gi * fcq, gbytes, true);
       } else if (i == NREC + 11 + NGEOM) {
-        bulk_g2s(smem_addr(sLR), m.face_lr + T.face_start, lbytes, bar);
+        emit(smem_addr(sLR), m.face_lr + TT.face_start, lbytes, true);
       } else {
         const int s = i - (NREC + 11 + NGEOM + 1);
-        bulk_g2s(smem_addr(sSlot + s * SC), m.slot_face + (size_t)s * m.slot_stride + (T.cell_start - sshift), sbytes, bar);
+        emit(smem_addr(sSlot + s * SC), m.slot_face + (size_t)s * m.slot_stride + (TT.cell_start - ssh), sbytes, true);
       }
     }
+  };
+  if (tid < 32) {
+    const unsigned vbytes = (unsigned)hb * 8u, gbytes = fcp * 8u, lbytes = fcp * 4u;
+    const unsigned sbytes = (unsigned)((sshift + nc + 7) & ~7) * 2u;
+    const int nrk = 1 + (a.kind != 2 ? 5 : 0) + (a.kind != 0 ? 5 : 0);
+    if (tid == 0) mbar_arrive_expect_tx(bar, (NREC + (RKS ? nrk : 0)) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes);
+    __syncwarp();
+    if (MA_FLUX_EXPERIMENT == 3) {  // the same bytes as four large requests (timing experiment)
+      if (tid == 0) asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(4u * 16384u) : "memory");
+      __syncwarp();
+      if (tid < 4)
+        bulk_g2s(smem_addr(sRec) + tid * 16384u, a.grad + (size_t)((blockIdx.x & 8191u) * 4u + tid) * 2048u, 16384u, bar);
+      if (tid < 32) {
+        const unsigned total = (NREC + (RKS ? nrk : 0)) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes;
+        if (tid == 0) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+      }
+    } else
+    for_each_run(T, [&](unsigned dst, const void *src, unsigned bytes, bool staged) {
+      if (MA_FLUX_EXPERIMENT == 2 && (const void *)src != (const void *)(m.face_lr + T.face_start) &&
+          !((const char *)src >= (const char *)m.slot_face && (const char *)src < (const char *)(m.slot_face + 6 * (size_t)m.slot_stride))) {
+        if (staged) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        return;
+      }
+      if (staged)
+        bulk_g2s(dst, src, bytes, bar);
+      else  // phase 2 reads this run from global memory: have it in L2 by then
+        bulk_prefetch_l2(src, bytes);
+    });
   }
   // the outside-cell record of this thread's cut face: registers, in flight together with the copies
   double orec[NREC];
@@ -925,7 +995,37 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     }
     mbar_cp_async_arrive(bar);
   }
-  if (my_outside >= 0) gather_outside(my_outside);
+  if (MA_FLUX_EXPERIMENT == 2) {
+#pragma unroll
+    for (int k = 0; k < NREC; ++k) orec[k] = 1.0 + k;
+  } else if (my_outside >= 0)
+    gather_outside(my_outside);
+  if (XC == 0 && CUT2 > 0 && my_outside2 >= 0) {
+    const int c = my_outside2;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) prefetch_l2(a.V + (size_t)k * m.stride + c);
+    if (R::GRAD) {
+#pragma unroll
+      for (int k = 0; k < 15; ++k) prefetch_l2(a.grad + (size_t)k * m.stride + c);
+    }
+    if (SECOND) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) prefetch_l2(a.lim + (size_t)k * m.stride + c);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) prefetch_l2(m.cell_xyz + (size_t)d * m.stride + c);
+    }
+  }
+  if (MA_FLUX_PREFETCH_AHEAD > 0 && tid < 32) {
+    // the operand runs of the tile a CTA MA_FLUX_PREFETCH_AHEAD positions later will copy: into L2 now (its descriptor
+    // is an L2 hit, prefetch_tile_header), so that CTA's bulk copies are served from L2
+    const int nxt = (int)blockIdx.x + MA_FLUX_PREFETCH_AHEAD;
+    if (nxt < (int)gridDim.x) {
+      const TileInfoDev P = m.tiles[tile_begin + nxt];
+      for_each_run(P, [&](unsigned, const void *src, unsigned bytes, bool) {
+        if (bytes >= MA_FLUX_PREFETCH_MIN_BYTES) bulk_prefetch_l2(src, bytes);
+      });
+    }
+  }
   mbar_wait(bar, 0);
 
   // ---- phase 1: one flux per tile face.  Work item w: cut face cut_start + w for w < nh, closed / boundary face
@@ -955,6 +1055,13 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];  // this thread's own column: geometry is dead
   };
   int w = tid;
+  if (MA_FLUX_EXPERIMENT == 1 || MA_FLUX_EXPERIMENT == 3) {
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < NREC; ++k) acc += orec[k];
+    if (acc == 1.2345e300) sG[tid] = acc;  // keeps the gather alive
+    w = nf;
+  }
   if (w < nh) {  // first cut face of this thread: outside record in registers
     cut_face(T.cut_start + w, RRec{orec});
     w += blockDim.x;
@@ -963,7 +1070,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     if (XC > 0 && blockDim.x == CAP::FLUX_THREADS && w - (int)blockDim.x < XC) {
       cut_face(T.cut_start + w, XRec{sOut + (w - (int)blockDim.x)});
     } else {
-      gather_outside(__ldg(halo_ids + w));
+      gather_outside(w == tid + CAP::FLUX_THREADS && my_outside2 >= 0 ? my_outside2 : __ldg(halo_ids + w));
       cut_face(T.cut_start + w, RRec{orec});
     }
   }
@@ -1027,12 +1134,12 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   for (int lc = tid; lc < nc; lc += blockDim.x) {
     const int c = T.cell_start + lc;
     const int p = shift + lc;
-    const double dtv = a.dt * rcp(sRK[p]);
+    const double dtv = a.dt * rcp(RKS ? sRK[p] : __ldg(m.cell_vol + c));
     double Rs[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       const unsigned sf = sSlot[s * SC + sshift + lc];
-      const int e = (int)(sf & 0x3fffu);
+      const int e = MA_FLUX_EXPERIMENT == 3 ? (int)(sf & 0xffu) : (int)(sf & 0x3fffu);
       const double sg = (sf & 0x8000u) ? dtv : -dtv;  // Flux.h:172-178: left slot holds -flux, right slot +flux
 #pragma unroll
       for (int k = 0; k < 5; ++k) Rs[k] = fma(sg, sG[k * FC + e], Rs[k]);
@@ -1041,20 +1148,22 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     if (a.kind == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double w0 = sRK[(1 + k) * RC + p];
+        const double w0 = RKS ? sRK[(1 + k) * RC + p] : __ldg(a.Un + (size_t)k * m.stride + c);
         a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], w0);
         Wn[k] = fma(a.alpha_next, Rs[k], w0);
       }
     } else if (a.kind == 1) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], sRK[(6 + k) * RC + p]);
-        Wn[k] = fma(a.alpha_next, Rs[k], sRK[(1 + k) * RC + p]);
+        const double acc = RKS ? sRK[(6 + k) * RC + p] : a.Acc[(size_t)k * m.stride + c];
+        const double un = RKS ? sRK[(1 + k) * RC + p] : __ldg(a.Un + (size_t)k * m.stride + c);
+        a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], acc);
+        Wn[k] = fma(a.alpha_next, Rs[k], un);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        Wn[k] = fma(a.beta, Rs[k], sRK[(6 + k) * RC + p]);
+        Wn[k] = fma(a.beta, Rs[k], RKS ? sRK[(6 + k) * RC + p] : a.Acc[(size_t)k * m.stride + c]);
         a.Un[(size_t)k * m.stride + c] = Wn[k];
       }
     }
@@ -1258,6 +1367,8 @@ static cudaError_t prepare_tma() {
   cudaError_t e;
 #define MA_SET(K, BYTES)                                                                   \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));  \
+  if (e != cudaSuccess) return e;                                                          \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
   if (e != cudaSuccess) return e;
   MA_SET((grad_limiter_tma_kernel<true, CAP, true>), grad_tma_smem<CAP>(true))
   MA_SET((grad_limiter_tma_kernel<false, CAP, true>), grad_tma_smem<CAP>(false))

@@ -37,6 +37,55 @@ inline uint64_t spread3(uint64_t v) {
   v = (v | v << 2) & 0x1249249249249249ULL;
   return v;
 }
+
+// Bank-conflict-aware order of one group of tile faces (FAST staged flux kernel).  Work item q of the group is
+// evaluated by lane (lane0 + q) of the CTA; a 64-bit shared-memory load is served half-warp by half-warp, one
+// wavefront when the 16 lanes address 16 different double-words modulo 16.  Every item reads the staged records of
+// up to two cells (positions a, b; -1 = none) in load streams `sa`, `sb` (lanes of different streams execute
+// different instructions: interior / boundary / cut-left / cut-right).  Greedy: walk the lanes in order and give
+// each the earliest unplaced item (within a window) whose positions collide with nothing already in its half-warp.
+// The slot-ordered gather makes results independent of the face order (tests: test_result_independent_of_tiling).
+struct PackItem {
+  int a, b;   // staged-cell positions read by this face (b < 0: only a)
+  int sa, sb; // stream of each read, 0..3
+};
+inline void pack_conflict_free(const std::vector<PackItem> &items, int lane0, std::vector<int> &order) {
+  const int n = (int)items.size();
+  order.clear();
+  order.reserve(n);
+  // lanes of one kind (code path) stay together: a warp that holds two kinds executes both paths
+  std::vector<int> seg;
+  uint16_t mask[4] = {0, 0, 0, 0};
+  const int window = 128;
+  for (int kind = 0; kind < 4; ++kind) {
+    seg.clear();
+    for (int j = 0; j < n; ++j)
+      if (items[j].sa == kind) seg.push_back(j);
+    const int m = (int)seg.size();
+    std::vector<char> used(m, 0);
+    int first = 0;
+    for (int q = 0; q < m; ++q) {
+      if (((lane0 + (int)order.size()) & 15) == 0) mask[0] = mask[1] = mask[2] = mask[3] = 0;
+      while (first < m && used[first]) ++first;
+      int pick = first, seen = 0;
+      for (int j = first; j < m && seen < window; ++j) {
+        if (used[j]) continue;
+        ++seen;
+        const PackItem &it = items[seg[j]];
+        if (mask[it.sa] >> (it.a & 15) & 1) continue;
+        if (it.b >= 0 && (mask[it.sb] >> (it.b & 15) & 1)) continue;
+        pick = j;
+        break;
+      }
+      const PackItem &it = items[seg[pick]];
+      mask[it.sa] |= (uint16_t)(1u << (it.a & 15));
+      if (it.b >= 0) mask[it.sb] |= (uint16_t)(1u << (it.b & 15));
+      used[pick] = 1;
+      order.push_back(seg[pick]);
+    }
+  }
+}
+
 inline uint64_t morton3(long x, long y, long z) { return spread3((uint64_t)x) << 2 | spread3((uint64_t)y) << 1 | spread3((uint64_t)z); }
 
 }  // namespace
@@ -183,6 +232,9 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
 
   const char *order_env = getenv("MINIAERO_TILE_ORDER");  // experiment knob: "linear" = x-major tile order
   const bool linear_order = order_env && !strcmp(order_env, "linear");
+  const char *sw_env = getenv("MINIAERO_CELL_SWIZZLE");  // experiment knob: 0 = plain z-fastest order inside a tile
+  const bool swizzle = !with_tangents && L.tile_dims[0] == 4 && L.tile_dims[1] == 4 && L.tile_dims[2] == 8 &&
+                       !(sw_env && sw_env[0] == '0');
   struct Key {
     uint64_t tile;
     uint32_t local;
@@ -199,7 +251,16 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
       l[d] = q[d] % L.tile_dims[d];
     }
     keys[c].tile = linear_order ? ((uint64_t)t[0] * ntile_d[1] + t[1]) * ntile_d[2] + t[2] : morton3(t[0], t[1], t[2]);
-    keys[c].local = (uint32_t)((l[0] * L.tile_dims[1] + l[1]) * L.tile_dims[2] + l[2]);
+    uint32_t local = (uint32_t)((l[0] * L.tile_dims[1] + l[1]) * L.tile_dims[2] + l[2]);
+    if (swizzle) {
+      // 4 x 4 x 8 bricks, z fastest: the cells of a brick SURFACE (the own cells of the cut faces) would share few
+      // shared-memory banks (z surface: 2 of the 16 double-word residues, y surface: 8).  XOR-ing the low four bits
+      // with a function of the 16-cell group index h = (x, y / 2) spreads every surface over all 16 residues while
+      // aligned 8-cell z runs stay contiguous (the cut-face gathers keep their sector efficiency).
+      const uint32_t h = local >> 4;
+      local ^= ((h >> 1) & 3u) | ((h & 1u) << 2) | (((h >> 2) & 1u) << 3);
+    }
+    keys[c].local = local;
     keys[c].cell = (int)c;
   }
   auto key_less = [](const Key &a, const Key &b) {
@@ -357,25 +418,61 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.tile_halo.assign((size_t)n_tiles * L.halo_stride, -1);
   const char *fo_env = getenv("MINIAERO_FACE_ORDER");
   const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
+  const bool pack = !by_cell && !(fo_env && !strcmp(fo_env, "slot"));
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
     const size_t fcp = (size_t)round_up(T.face_count, 16);
     const int shift = T.cell_start & 1, halo_base = round_up(shift + T.cell_count, 2);
-    int e_closed = 0, e_cut = T.cut_start;
-    // closed / boundary faces first, cut faces last; each group in (cell, slot) order: the face sweep then
-    // walks cells in order and every cell's data is touched within a short window
-    // face order inside each group: by slot (direction), then by cell — consecutive faces then read consecutive
-    // own cells and consecutive neighbours (conflict-free shared-memory banks in the staged kernels);
-    // MINIAERO_FACE_ORDER=cell keeps (cell, slot) order (the gather kernels' L1 locality)
+    // closed / boundary faces first, cut faces last.  Inside each group the faces are listed by slot (direction),
+    // then by cell — consecutive faces read consecutive own cells and consecutive neighbours — and, for the staged
+    // FAST kernels, that list is re-packed half-warp by half-warp so that the 16 lanes of a shared-memory wavefront
+    // read 16 different banks (pack_conflict_free; MINIAERO_FACE_ORDER=slot keeps the plain list).
+    // MINIAERO_FACE_ORDER=cell (and STRICT) keeps (cell, slot) order (the gather kernels' L1 locality).
+    struct Emit {
+      int c, s;
+    };
+    std::vector<Emit> group[2];  // 0 closed / boundary, 1 cut
+    std::vector<PackItem> pitems[2];
     for (int it = 0; it < 6 * T.cell_count; ++it) {
       const int c = T.cell_start + (by_cell ? it / 6 : it % T.cell_count);
       const int s = by_cell ? it % 6 : it / T.cell_count;
+      if (!emits(T, c, s)) continue;
+      const bool cut = is_cut(T, c, s);
+      group[cut].push_back({c, s});
+      if (pack) {
+        const uint32_t ref = cf[(size_t)L.new2old[c] * 6 + s];
+        const int side = (int)(ref & 1), own = shift + (c - T.cell_start);
+        const int oth = other_cell(ref);
+        PackItem pi;
+        if (cut) {
+          pi = {own, -1, side == 0 ? 2 : 3, 0};
+        } else if (oth < 0) {
+          pi = {own, -1, 2, 0};
+        } else {
+          const int op = shift + (L.old2new[oth] - T.cell_start);
+          pi = side == 0 ? PackItem{own, op, 0, 1} : PackItem{op, own, 0, 1};
+        }
+        pitems[cut].push_back(pi);
+      }
+    }
+    std::vector<int> porder[2];
+    for (int g = 0; g < 2; ++g) {
+      if (pack) {
+        // the closed group follows the cut group in the kernel's work-item numbering
+        pack_conflict_free(pitems[g], g == 0 ? (int)(group[1].size() & 15) : 0, porder[g]);
+      } else {
+        porder[g].resize(group[g].size());
+        for (size_t i = 0; i < group[g].size(); ++i) porder[g][i] = (int)i;
+      }
+    }
+    for (int g = 0; g < 2; ++g)
+    for (size_t q = 0; q < group[g].size(); ++q) {
+      const int c = group[g][porder[g][q]].c, s = group[g][porder[g][q]].s;
       const int oldc = L.new2old[c];
       {
-        if (!emits(T, c, s)) continue;
-        const bool cut = is_cut(T, c, s);
-        const int e = cut ? e_cut++ : e_closed++;
+        const bool cut = g == 1;
+        const int e = (cut ? T.cut_start : 0) + (int)q;
         const uint32_t ref = cf[(size_t)oldc * 6 + s];
         const int side = (int)(ref & 1);
         const FaceSrc src = face_src(ref);

@@ -124,6 +124,15 @@ struct ma_solver {
   ma_timing tm;
   double sim_time = 0.0;
   long time_it = 0;
+  // ma_solver_submit pipeline: two upload and two download staging buffers, one copy stream per direction
+  struct Pipe {
+    cudaStream_t cin = nullptr, cout = nullptr;
+    double *d_in[2] = {nullptr, nullptr}, *d_out[2] = {nullptr, nullptr};
+    cudaEvent_t in_ready[2] = {nullptr, nullptr}, in_free[2] = {nullptr, nullptr};
+    cudaEvent_t out_ready[2] = {nullptr, nullptr}, out_free[2] = {nullptr, nullptr};
+    long submitted = 0;
+    bool ready = false;
+  } pipe;
 };
 
 namespace {
@@ -372,6 +381,17 @@ void ma_solver_destroy(ma_solver *S) {
     if (pp.a) cudaEventDestroy(pp.a);
     if (pp.b) cudaEventDestroy(pp.b);
   }
+  if (S->pipe.cin) cudaStreamSynchronize(S->pipe.cin);
+  if (S->pipe.cout) cudaStreamSynchronize(S->pipe.cout);
+  for (int i = 0; i < 2; ++i) {
+    if (S->pipe.d_in[i]) cudaFree(S->pipe.d_in[i]);
+    if (S->pipe.d_out[i]) cudaFree(S->pipe.d_out[i]);
+    cudaEvent_t pe[] = {S->pipe.in_ready[i], S->pipe.in_free[i], S->pipe.out_ready[i], S->pipe.out_free[i]};
+    for (cudaEvent_t e : pe)
+      if (e) cudaEventDestroy(e);
+  }
+  if (S->pipe.cin) cudaStreamDestroy(S->pipe.cin);
+  if (S->pipe.cout) cudaStreamDestroy(S->pipe.cout);
   if (S->own_cs && S->cs) cudaStreamDestroy(S->cs);
   if (S->own_stream && S->st) cudaStreamDestroy(S->st);
   delete S;
@@ -631,8 +651,79 @@ int ma_solver_solve(ma_solver *S) {
 int ma_solver_synchronize(ma_solver *S) {
   if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
   MA_CUDA_TRY(cudaSetDevice(S->device));
+  if (S->pipe.cin) MA_CUDA_TRY(cudaStreamSynchronize(S->pipe.cin));
   MA_CUDA_TRY(cudaStreamSynchronize(S->cs));
   MA_CUDA_TRY(cudaStreamSynchronize(S->st));
+  if (S->pipe.cout) MA_CUDA_TRY(cudaStreamSynchronize(S->pipe.cout));
+  MA_CUDA_TRY(cudaGetLastError());
+  collect_profile(S);  // event pairs of submitted (unsynchronised) steps
+  return MA_OK;
+}
+
+// Asynchronous ensemble member (see the header).  Three streams: the upload of member i+1 and the download of
+// member i-1 run while member i is being stepped; the staging buffers are double-buffered and handed over by events.
+int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, int nsteps) {
+  if (!S || !state_in || !state_out) return ma_set_error(MA_ERR_INVALID, "ma_solver_submit: null argument");
+  if (nsteps < 0) return ma_set_error(MA_ERR_INVALID, "nsteps must be >= 0");
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  ma_solver::Pipe &P = S->pipe;
+  const size_t elems = (size_t)S->n_owned * 5;
+  if (!P.ready) {
+    MA_CUDA_TRY(cudaStreamCreateWithFlags(&P.cin, cudaStreamNonBlocking));
+    MA_CUDA_TRY(cudaStreamCreateWithFlags(&P.cout, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      int rc = dev_alloc(&P.d_in[i], elems, &S->device_bytes);
+      if (rc) return rc;
+      rc = dev_alloc(&P.d_out[i], elems, &S->device_bytes);
+      if (rc) return rc;
+      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.in_ready[i], cudaEventDisableTiming));
+      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.in_free[i], cudaEventDisableTiming));
+      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.out_ready[i], cudaEventDisableTiming));
+      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.out_free[i], cudaEventDisableTiming));
+    }
+    P.ready = true;
+  }
+  const Api K = api_of(S->strict);
+  const int slot = (int)(P.submitted & 1);
+  const bool reuse = P.submitted >= 2;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((elems + threads - 1) / threads);
+  // upload (copy-in stream)
+  if (reuse) MA_CUDA_TRY(cudaStreamWaitEvent(P.cin, P.in_free[slot], 0));
+  MA_CUDA_TRY(cudaMemcpyAsync(P.d_in[slot], state_in, elems * sizeof(double), cudaMemcpyHostToDevice, P.cin));
+  MA_CUDA_TRY(cudaEventRecord(P.in_ready[slot], P.cin));
+  // compute (solver stream)
+  int rc = wait_state_exchange(S);
+  if (rc) return rc;
+  MA_CUDA_TRY(cudaStreamWaitEvent(S->st, P.in_ready[slot], 0));
+  caller_to_soa_kernel<<<blocks, threads, 0, S->st>>>(P.d_in[slot], S->stride, 5, S->n_owned, S->d_old2new, S->d_Un);
+  MA_CUDA_TRY(cudaGetLastError());
+  MA_CUDA_TRY(cudaEventRecord(P.in_free[slot], S->st));
+  MA_CUDA_TRY(K.prims(S->dm, S->d_Un, S->d_V[S->vcur], S->st));
+  rc = start_state_exchange(S, S->d_V[S->vcur]);
+  if (rc) return rc;
+  for (int it = 0; it < nsteps; ++it) {
+    S->sim_time += S->opt.dt;
+    S->time_it++;
+    for (int k = 0; k < 4; ++k) {
+      rc = run_stage(S, K, k);
+      if (rc) return rc;
+    }
+  }
+  rc = wait_state_exchange(S);
+  if (rc) return rc;
+  if (reuse) MA_CUDA_TRY(cudaStreamWaitEvent(S->st, P.out_free[slot], 0));
+  soa_to_caller_kernel<<<blocks, threads, 0, S->st>>>(S->d_Un, S->stride, 5, S->n_owned, S->d_old2new, P.d_out[slot]);
+  MA_CUDA_TRY(cudaGetLastError());
+  MA_CUDA_TRY(cudaEventRecord(P.out_ready[slot], S->st));
+  // download (copy-out stream)
+  MA_CUDA_TRY(cudaStreamWaitEvent(P.cout, P.out_ready[slot], 0));
+  MA_CUDA_TRY(cudaMemcpyAsync(state_out, P.d_out[slot], elems * sizeof(double), cudaMemcpyDeviceToHost, P.cout));
+  MA_CUDA_TRY(cudaEventRecord(P.out_free[slot], P.cout));
+  P.submitted++;
+  S->tm.steps += nsteps;
+  S->tm.cell_updates += (long long)nsteps * S->n_owned;
+  S->tm.kernel_launches += 3;
   return MA_OK;
 }
 

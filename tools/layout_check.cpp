@@ -1,0 +1,159 @@
+// Host-side check of the tile layout (no GPU): invariants of the tile-packed face lists and slot maps, and the
+// shared-memory wavefront count the staged flux kernel would see (64-bit loads, half-warp by half-warp, one wavefront
+// per distinct double-word modulo 16 ... the model of DESIGN.md §3).
+//   g++ -O2 -std=c++17 -fopenmp -Iinclude -Iminiaero_b200/csrc tools/layout_check.cpp miniaero_b200/build/{layout,host_mesh,host_common}.o -o /tmp/layout_check
+//   /tmp/layout_check NX NY NZ [tx ty tz] [threads]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "layout.h"
+#include "miniaero_b200.h"
+
+static int wavefronts16(const int *pos, int n) {  // wavefronts of one half-warp: max multiplicity over 16 residues
+  int cnt[16] = {0};
+  int mx = 0;
+  for (int i = 0; i < n; ++i)
+    if (pos[i] >= 0) mx = std::max(mx, ++cnt[pos[i] & 15]);
+  return mx;
+}
+
+int main(int argc, char **argv) {
+  ma_options opt;
+  ma_options_default(&opt);
+  opt.problem_type = 0;
+  opt.lx = 0.3048, opt.ly = 1.0, opt.lz = 1.0;
+  opt.nx = argc > 1 ? atoi(argv[1]) : 64, opt.ny = argc > 2 ? atoi(argv[2]) : 32, opt.nz = argc > 3 ? atoi(argv[3]) : 32;
+  int td[3] = {argc > 4 ? atoi(argv[4]) : 4, argc > 5 ? atoi(argv[5]) : 4, argc > 6 ? atoi(argv[6]) : 8};
+  const int threads = argc > 7 ? atoi(argv[7]) : 128;
+  ma_mesh_storage *mh = nullptr;
+  if (ma_mesh_generate(&opt, 0, 1, &mh)) return printf("mesh: %s\n", ma_last_error()), 1;
+  const ma_mesh *mesh = ma_mesh_view(mh);
+  ma::HostLayout L;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (ma::build_layout(*mesh, td, false, L)) return printf("layout: %s\n", ma_last_error()), 1;
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  printf("cells %d tiles %d tile faces %ld layout %.2f s\n", L.n_owned, L.n_tiles, L.n_tile_faces_real, sec);
+  // ---- invariants
+  long bad = 0;
+  std::vector<int> seen((size_t)mesh->internal_faces.nfaces, 0);
+  for (int k = 0; k < L.n_tiles; ++k) {
+    const ma::TileInfo &T = L.tiles[k];
+    const int shift = T.cell_start & 1, hb = ((shift + T.cell_count + 1) & ~1);
+    for (int e = 0; e < T.face_count; ++e) {
+      const size_t j = (size_t)T.face_start + e;
+      const int l = L.face_left[j], r = L.face_right[j];
+      const unsigned lr = L.face_lr[j];
+      const int pl = lr & 0xffff, pr = lr >> 16;
+      const bool cut = e >= T.cut_start;
+      auto pos_of = [&](int c) { return (c >= T.cell_start && c < T.cell_start + T.cell_count) ? shift + c - T.cell_start : -1; };
+      if (r < 0) {  // boundary
+        if (cut || pos_of(l) != pl || pr != 0xFFFF - (-1 - r)) ++bad;
+      } else if (!cut) {
+        if (pos_of(l) != pl || pos_of(r) != pr) ++bad;
+      } else {
+        const int h = hb + (e - T.cut_start);
+        const int out = L.tile_halo[(size_t)T.halo_start + (e - T.cut_start)];
+        if (pos_of(l) >= 0) {
+          if (pos_of(l) != pl || pr != h || out != r || pos_of(r) >= 0) ++bad;
+        } else {
+          if (pos_of(r) != pr || pl != h || out != l) ++bad;
+        }
+      }
+    }
+    // slot maps: every (cell, slot) points at a face of this tile that has the cell on the stated side
+    for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c)
+      for (int s = 0; s < 6; ++s) {
+        const unsigned sf = L.slot_face[(size_t)s * L.slot_stride + c];
+        const int e = sf & 0x3fff, side = (sf >> 15) & 1;
+        if (e >= T.face_count) { ++bad; continue; }
+        const size_t j = (size_t)T.face_start + e;
+        const int cell = side ? L.face_right[j] : L.face_left[j];
+        if (cell != c) ++bad;
+        if (((sf >> 14) & 1) != (L.face_right[j] < 0)) ++bad;
+      }
+  }
+  printf("invariant violations: %ld\n", bad);
+  // ---- wavefront model of the staged flux kernel
+  long ideal1 = 0, wf1 = 0, ideal2 = 0, wf2 = 0, paths = 0, warps = 0;
+  for (int k = 0; k < L.n_tiles; ++k) {
+    const ma::TileInfo &T = L.tiles[k];
+    const int nh = T.face_count - T.cut_start, nf = T.face_count;
+    const int shift = T.cell_start & 1, hb = ((shift + T.cell_count + 1) & ~1);
+    for (int w0 = 0; w0 < nf; w0 += 16) {  // work items of one half-warp (threads is a multiple of 16)
+      int p[4][16];
+      for (int st = 0; st < 4; ++st)
+        for (int i = 0; i < 16; ++i) p[st][i] = -1;
+      for (int i = 0; i < 16 && w0 + i < nf; ++i) {
+        const int w = w0 + i;
+        const int e = w < nh ? T.cut_start + w : w - nh;
+        const size_t j = (size_t)T.face_start + e;
+        const unsigned lr = L.face_lr[j];
+        const int pl = lr & 0xffff, pr = lr >> 16;
+        if (w < nh) {
+          if (pr >= hb) p[2][i] = pl; else p[3][i] = pr;
+        } else if (pr >= 0xFFF0) {
+          p[2][i] = pl;
+        } else {
+          p[0][i] = pl, p[1][i] = pr;
+        }
+      }
+      for (int st = 0; st < 4; ++st) {
+        const int m = wavefronts16(p[st], 16);
+        wf1 += m;
+        ideal1 += m > 0;
+      }
+    }
+    for (int w0 = 0; w0 < nf; w0 += 32) {  // code paths per warp: cut-left, cut-right, interior, boundary
+      int kinds = 0;
+      for (int i = 0; i < 32 && w0 + i < nf; ++i) {
+        const int w = w0 + i;
+        const int e = w < nh ? T.cut_start + w : w - nh;
+        const unsigned lr = L.face_lr[(size_t)T.face_start + e];
+        const int pr = lr >> 16;
+        kinds |= w < nh ? (pr >= hb ? 1 : 2) : (pr >= 0xFFF0 ? 8 : 4);
+      }
+      paths += __builtin_popcount(kinds);
+      ++warps;
+    }
+    for (int c0 = 0; c0 < T.cell_count; c0 += 16)
+      for (int s = 0; s < 6; ++s) {
+        int p[16];
+        for (int i = 0; i < 16; ++i)
+          p[i] = c0 + i < T.cell_count ? (int)(L.slot_face[(size_t)s * L.slot_stride + T.cell_start + c0 + i] & 0x3fff) : -1;
+        wf2 += wavefronts16(p, 16);
+        ideal2 += 1;
+      }
+  }
+  // gradient kernel: thread per own cell; per slot it reads 6 geometry values of face e(s, c) and 5 primitives of
+  // the neighbour at staged position nb(s, c)
+  long gi = 0, gw_e = 0, gw_n = 0;
+  for (int k = 0; k < L.n_tiles; ++k) {
+    const ma::TileInfo &T = L.tiles[k];
+    for (int c0 = 0; c0 < T.cell_count; c0 += 16)
+      for (int s = 0; s < 6; ++s) {
+        int pe[16], pn[16];
+        for (int i = 0; i < 16; ++i) {
+          const bool in = c0 + i < T.cell_count;
+          const size_t idx = (size_t)s * L.slot_stride + T.cell_start + c0 + i;
+          pe[i] = in ? (int)(L.slot_face[idx] & 0x3fff) : -1;
+          pn[i] = in && L.slot_nbr[idx] != 0xFFFF ? (int)L.slot_nbr[idx] : -1;
+        }
+        gw_e += wavefronts16(pe, 16);
+        gw_n += std::max(1, wavefronts16(pn, 16));
+        ++gi;
+      }
+  }
+  printf("gradient kernel: geometry-read wavefronts / ideal %.3f, neighbour-read %.3f, weighted (6:5) %.3f\n",
+         (double)gw_e / gi, (double)gw_n / gi, (6.0 * gw_e + 5.0 * gw_n) / (11.0 * gi));
+  (void)threads;
+  printf("code paths per warp of 32 work items: %.3f\n", (double)paths / warps);
+  printf("phase 1 record-read wavefronts / ideal: %.3f   phase 2 flux-read wavefronts / ideal: %.3f\n",
+         (double)wf1 / ideal1, (double)wf2 / ideal2);
+  printf("weighted (28 reads per record stream, 5 per flux read): %.3f\n",
+         (28.0 * wf1 + 5.0 * wf2) / (28.0 * ideal1 + 5.0 * ideal2));
+  ma_mesh_free(mh);
+  return bad != 0;
+}

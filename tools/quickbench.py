@@ -60,5 +60,8 @@ if __name__ == '__main__':
         run(*N, 1, 0, tag='o2 inviscid')
         run(*N, 0, 0, tag='o1 inviscid')
         run(256, 128, 64, 1, 1, ptype=1, lx=2.0, ly=0.008, lz=1.0, dt=3e-8, tag='flatplate')
+    elif mode == 'one':  # python tools/quickbench.py one NX NY NZ [tag]
+        nx, ny, nz = (int(x) for x in sys.argv[2:5])
+        run(nx, ny, nz, 1, 1, tag=sys.argv[5] if len(sys.argv) > 5 else '')
     elif mode == 'big':
         run(512, 512, 256, 1, 1, tag='sod_o2_visc 67M')
