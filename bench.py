@@ -16,6 +16,8 @@ Workloads (all inputs are generated in code, data = "synthetic
                viscous term on: the "full second-order viscous RK4 step" of the north star).  DEFAULT.
   sod_o2       BASELINE configs[1]: the same mesh, second order, inviscid.
   flatplate    BASELINE configs[2]: viscous flat plate 1024x512x128 (NoSlip/Inflow/Tangent/Extrapolate).
+  flatplate_strong  BASELINE configs[4]: the flat plate on a fixed 1024x512x512 global mesh split over the N GPUs
+               ("scaling": "strong"; not part of the default run).
 The default run also measures the other two single-GPU workloads for a few steps and reports them under
 "also" (N = 1 only).
 """
@@ -53,6 +55,12 @@ def workload_options(name, n_gpus, cells=None):
     if name == "flatplate":
         base = (1024, 512, 128)
         g = cells or tuple(b * s for b, s in zip(base, {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n_gpus]))
+        return dict(problem_type=1, lx=2.0 * g[0] / 1024.0, ly=0.032 * g[1] / 512.0, lz=1.0 * g[2] / 128.0, angle=0.0,
+                    nx=g[0], ny=g[1], nz=g[2], dt=3e-8, second_order_space=1, viscous=1)
+    if name == "flatplate_strong":
+        # BASELINE configs[4]: the viscous flat plate on a FIXED 1024 x 512 x 512 global mesh (268 M cells) split over
+        # the N GPUs (strong scaling; at N = 1 it needs ~162 GB of device and ~240 GB of host memory)
+        g = cells or (1024, 512, 512)
         return dict(problem_type=1, lx=2.0 * g[0] / 1024.0, ly=0.032 * g[1] / 512.0, lz=1.0 * g[2] / 128.0, angle=0.0,
                     nx=g[0], ny=g[1], nz=g[2], dt=3e-8, second_order_space=1, viscous=1)
     raise SystemExit("unknown workload %r" % name)
@@ -124,25 +132,25 @@ def reference_sample_dims(opt, steps_total, budget_s, cores):
     return best
 
 
-def run_reference(workload, steps, warmup, budget_s):
+def run_reference(workload, steps, warmup, budget_s, kind="cell", dims=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refrun
     cores = host_cores()
     base = workload_options(workload, 1)
-    d = reference_sample_dims(base, steps + warmup, budget_s, cores)
+    d = dims or reference_sample_dims(base, steps + warmup, budget_s, cores)
     full = (base["nx"], base["ny"], base["nz"])
     inp = dict(problem_type=base["problem_type"], lx=base["lx"] * d[0] / full[0], ly=base["ly"] * d[1] / full[1],
                lz=base["lz"] * d[2] / full[2], angle=base["angle"], nx=d[0], ny=d[1], nz=d[2], ntimesteps=steps + warmup,
                dt=base["dt"], output_results=0, output_frequency=10 ** 9, second_order=base["second_order_space"],
                viscous=base["viscous"])
-    exe = refrun.ref_binary("cell", omp=True)
+    exe = refrun.ref_binary(kind, omp=True)
     if exe is None:
         return None
     tmp = tempfile.mkdtemp(prefix="miniaero_bench_ref_")
     log = os.path.join(tmp, "launch.log")
     os.environ["MINIAERO_LAUNCH_LOG"] = log
     try:
-        refrun.run_reference(inp, kind="cell", omp=True, threads=cores, dump=False, workdir=tmp)
+        refrun.run_reference(inp, kind=kind, omp=True, threads=cores, dump=False, workdir=tmp)
     finally:
         os.environ.pop("MINIAERO_LAUNCH_LOG", None)
     ends, functors = [], {}
@@ -411,11 +419,17 @@ def gpu_arm(args):
                    "sample": "%s physics on a %dx%dx%d mesh (%d cells), 1 warm-up + 3 timed RK4 steps of the unmodified "
                              "reference (-DCELL_FLUX, OpenMP static loop over %d threads)" % (
                                  args.workload, r["dims"][0], r["dims"][1], r["dims"][2], r["cells"], r["cores"])}
+            # the reference Makefile's default build (-DATOMICS_FLUX: atomic face-to-cell accumulation), same sample
+            ra = run_reference(args.workload, 3, 1, budget_s=args.cpu_budget, kind="atomics", dims=tuple(r["dims"]))
+            if ra is not None:
+                cpu["atomics_flux_build"] = {"value": ra["value"], "what": "the same sample with the reference "
+                                             "Makefile's default -DATOMICS_FLUX (nondeterministic summation order)"}
 
     if rank == 0:
         line = {"metric": "cell-updates/sec (RK4 steps x cells) FP64", "value": value, "unit": "cell-updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * step_s / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if args.workload.endswith("_strong") else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "mesh": [optd["nx"], optd["ny"], optd["nz"]],
                            "cells_per_gpu": n_owned, "ghost_cells_rank0": info["ghost_cells"], "blocks": info["nproc"],
                            "second_order": optd["second_order_space"], "viscous": optd["viscous"], "dt": optd["dt"],
@@ -440,7 +454,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sod_o2_visc", choices=["sod_o2_visc", "sod_o2", "flatplate"])
+    ap.add_argument("--workload", default="sod_o2_visc", choices=["sod_o2_visc", "sod_o2", "flatplate", "flatplate_strong"])
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="override the GLOBAL mesh (debugging only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-also", dest="also", action="store_false")

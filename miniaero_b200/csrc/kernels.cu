@@ -1128,13 +1128,29 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
 #pragma unroll
     for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];
   }
+  // RK operands of this thread's (first) cell when they are not staged: requested before the barrier — the face
+  // registers are dead here — so that the loads fly while the CTA's slower warps finish their faces
+  double pre_vol = 1.0, pre_un[5] = {0, 0, 0, 0, 0}, pre_acc[5] = {0, 0, 0, 0, 0};
+  if (!RKS && tid < nc) {
+    const int c = T.cell_start + tid;
+    pre_vol = __ldg(m.cell_vol + c);
+    if (a.kind != 2) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) pre_un[k] = __ldg(a.Un + (size_t)k * m.stride + c);
+    }
+    if (a.kind != 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) pre_acc[k] = a.Acc[(size_t)k * m.stride + c];
+    }
+  }
   __syncthreads();
 
   // ---- phase 2: slot-ordered gather, residual, RK update; the next stage state is stored as primitives
   for (int lc = tid; lc < nc; lc += blockDim.x) {
     const int c = T.cell_start + lc;
     const int p = shift + lc;
-    const double dtv = a.dt * rcp(RKS ? sRK[p] : __ldg(m.cell_vol + c));
+    const bool pre = lc == tid;  // first cell of the thread: operands already requested
+    const double dtv = a.dt * rcp(RKS ? sRK[p] : pre ? pre_vol : __ldg(m.cell_vol + c));
     double Rs[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
@@ -1148,22 +1164,22 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     if (a.kind == 0) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double w0 = RKS ? sRK[(1 + k) * RC + p] : __ldg(a.Un + (size_t)k * m.stride + c);
+        const double w0 = RKS ? sRK[(1 + k) * RC + p] : pre ? pre_un[k] : __ldg(a.Un + (size_t)k * m.stride + c);
         a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], w0);
         Wn[k] = fma(a.alpha_next, Rs[k], w0);
       }
     } else if (a.kind == 1) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const double acc = RKS ? sRK[(6 + k) * RC + p] : a.Acc[(size_t)k * m.stride + c];
-        const double un = RKS ? sRK[(1 + k) * RC + p] : __ldg(a.Un + (size_t)k * m.stride + c);
+        const double acc = RKS ? sRK[(6 + k) * RC + p] : pre ? pre_acc[k] : a.Acc[(size_t)k * m.stride + c];
+        const double un = RKS ? sRK[(1 + k) * RC + p] : pre ? pre_un[k] : __ldg(a.Un + (size_t)k * m.stride + c);
         a.Acc[(size_t)k * m.stride + c] = fma(a.beta, Rs[k], acc);
         Wn[k] = fma(a.alpha_next, Rs[k], un);
       }
     } else {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        Wn[k] = fma(a.beta, Rs[k], RKS ? sRK[(6 + k) * RC + p] : a.Acc[(size_t)k * m.stride + c]);
+        Wn[k] = fma(a.beta, Rs[k], RKS ? sRK[(6 + k) * RC + p] : pre ? pre_acc[k] : a.Acc[(size_t)k * m.stride + c]);
         a.Un[(size_t)k * m.stride + c] = Wn[k];
       }
     }

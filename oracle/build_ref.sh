@@ -10,6 +10,8 @@
 #   miniAero.atomics     -DATOMICS_FLUX   serial    : the reference Makefile's default build (noise floor)
 #   miniAero.atomics.omp -DATOMICS_FLUX   -fopenmp
 #   miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 over oracle/mpi_standin (N cooperating processes)
+#   unit_oracle          oracle/unit_oracle.cpp: the reference's device functions (Roe, viscous, primitives, limiters)
+#                        included from the reference headers and evaluated on arrays of inputs
 set -euo pipefail
 HERE="$(cd "$(dirname "$0")" && pwd)"
 REF="${MINIAERO_REFERENCE:-/root/reference/kokkos}"
@@ -35,3 +37,8 @@ build miniAero.atomics.omp -DATOMICS_FLUX -fopenmp
 # the reference's WITH_MPI path (block decomposition + ghost exchange) over the file-based MPI stand-in:
 # full-precision per-rank results for the multi-GPU parity tests
 build miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 -I$HERE/mpi_standin
+# unit oracle: a driver of ours around the reference's headers (no reference source is copied)
+if [ ! "$OUT/unit_oracle" -nt "$HERE/unit_oracle.cpp" ] || [ ! "$OUT/unit_oracle" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ]; then
+  g++ $COMMON -DCELL_FLUX "$HERE/unit_oracle.cpp" -o "$OUT/unit_oracle"
+  echo "built $OUT/unit_oracle"
+fi

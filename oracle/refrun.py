@@ -141,3 +141,18 @@ def numeric_text_diff(a, b, rel_tol=1e-3, floor=1e-6):
         rel = np.where(denom > 0, np.abs(a - b) / denom, 0.0)
     bad = big & (rel > rel_tol)
     return int(bad.any(axis=1).sum())
+
+
+def unit_oracle(function, rows):
+    """Evaluate one of the reference's device functions (oracle/unit_oracle.cpp: roe | viscous | primitives |
+    venkat | vanalbada) on an [n, width] array of inputs; returns the [n, out_width] outputs."""
+    exe = os.path.join(REF_DIR, "unit_oracle")
+    if not os.path.isfile(exe):
+        raise FileNotFoundError("%s not built (oracle/build_ref.sh needs /root/reference)" % exe)
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+        rows.tofile(fin)
+        subprocess.run([exe, function, fin, fout], check=True)
+        out = np.fromfile(fout, dtype=np.float64)
+    return out.reshape(rows.shape[0], -1)

@@ -3,6 +3,7 @@
 at the tolerances of tests/<case>/<case>_test.sh, and (b) reproduce, bit for bit, the full-precision golden
 vectors the GPU parity tests compare against (so those vectors provably come from this oracle)."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -112,3 +113,36 @@ def test_parallel_oracle_agrees_with_serial_oracle_to_roundoff():
         linf, l2 = parity.field_errors(g["r%d_step100" % r], serial[gids])
         worst = max(worst, linf, l2)
     assert worst < parity.TOL_100_STEPS, worst
+
+
+def test_unit_golden_vectors_come_from_the_reference_functions():
+    """tests/golden/unit_functions.npz = tests/unit_inputs.py pushed through the reference's own device functions
+    (oracle/_ref/unit_oracle: Roe_Flux.h, Viscous_Flux.h, GasModel.h, VenkatLimiter.h, VanAlbadaLimiter.h)."""
+    import unit_inputs
+    g = parity.golden("unit_functions")
+    for fn, rows in unit_inputs.make_inputs().items():
+        assert parity.max_ulp(rows, g[fn + "_in"]) == 0, fn
+        assert parity.max_ulp(refrun.unit_oracle(fn, rows), g[fn + "_out"]) == 0, fn
+    # the sample reaches every branch: Venkat's |du| <= 1e-40 -> 1, Van Albada's clamp, the Roe eigenvalue fix
+    assert (g["venkat_out"] == 1.0).sum() >= 64 and g["venkat_out"].max() > 1.0
+    assert (g["vanalbada_out"] == 1.0).any() and (g["vanalbada_out"] == 0.0).any()
+    x = g["roe_in"]
+    a = x[:, 10:13]
+    un = (x[:, 1:4] * a).sum(axis=1) / np.linalg.norm(a, axis=1)
+    c = np.sqrt(1.4 * 287.05 * x[:, 4])
+    assert (np.abs(un) < 0.05 * c).any() and (np.abs(np.abs(un) - c) < 0.05 * c).any()
+
+
+def test_fullsize_column_golden_comes_from_this_oracle():
+    """tests/golden/sod_fullsize_column.npz: the reference's x-line for the cell size of the 67 M-cell benchmark mesh,
+    and its own 16 lines agree to roundoff (the property tests/test_gpu_fullsize.py relies on)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_fullsize as mk
+    g = parity.golden("sod_fullsize_column")
+    out = refrun.run_reference(dict(mk.INP, ntimesteps=2), kind="cell")
+    sol = refrun.solution_from_dumps(out["dumps"]).reshape(mk.NX, 4, 4, 5)
+    assert parity.max_ulp(sol[:, 1, 1, :], g["line_step2"]) == 0
+    spread = np.abs(sol - sol[:, 1:2, 1:2, :]).max(axis=(0, 1, 2))
+    scale = np.abs(sol).max(axis=(0, 1, 2))
+    scale[1:4] = np.sqrt((sol[..., 1:4] ** 2).sum(axis=-1)).max()
+    assert (spread <= 1e-14 * scale).all()
