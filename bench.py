@@ -213,15 +213,31 @@ def reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def build_solver(ma, optd, rank, world, comm, local_rank, keep_mesh=False):
+def build_solver(ma, optd, rank, world, comm, local_rank, keep_mesh=False, mesh_path="structured"):
+    """mesh_path "structured": ma_solver_create_structured (layout from (i, j, k), geometry evaluated on the device);
+    "arrays": ma_mesh_generate + ma_solver_create (the reference-format arrays, re-packed and uploaded).  Same solver,
+    bit for bit (tests/test_gpu_structured.py)."""
     opt = ma.Options(ntimesteps=1, output_results=0, output_frequency=10 ** 9, **optd)
     t0 = time.perf_counter()
+    if mesh_path == "structured" and not keep_mesh:
+        solver = ma.TimeSolverExplicitRK4.from_options(opt, rank, world, device=local_rank, comm=comm)
+        t2 = time.perf_counter()
+        n = [optd["nx"], optd["ny"], optd["nz"]]
+        nproc, left = [1, 1, 1], world
+        while left > 1:   # Parallel3DMesh.C:247-303: bisect the largest remaining dimension
+            left //= 2
+            d = max(range(3), key=lambda k: (n[k], -k))
+            nproc[d] *= 2
+            n[d] = [optd["nx"], optd["ny"], optd["nz"]][d] // nproc[d]
+        info = {"mesh_seconds": 0.0, "layout_upload_seconds": t2 - t0, "owned_cells": solver.num_owned_cells,
+                "ghost_cells": solver.num_ghosts, "nlocal": n, "nproc": nproc, "mesh_path": "structured"}
+        return solver, opt, info
     mesh = ma.Parallel3DMesh.from_options(opt, rank, world).fillMeshData()
     t1 = time.perf_counter()
     solver = ma.TimeSolverExplicitRK4(mesh, opt, device=local_rank, comm=comm)
     t2 = time.perf_counter()
     info = {"mesh_seconds": t1 - t0, "layout_upload_seconds": t2 - t1, "owned_cells": mesh.num_owned_cells,
-            "ghost_cells": mesh.num_ghosts, "nlocal": list(mesh.nlocal), "nproc": list(mesh.nproc)}
+            "ghost_cells": mesh.num_ghosts, "nlocal": list(mesh.nlocal), "nproc": list(mesh.nproc), "mesh_path": "arrays"}
     if not keep_mesh:
         solver.release_mesh()
         del mesh
@@ -294,12 +310,12 @@ def gpu_arm(args):
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 64 << 30
-    per_rank = 900.0 * optd["nx"] * optd["ny"] * optd["nz"] / world
+    per_rank = (320.0 if args.mesh_path == "structured" else 900.0) * optd["nx"] * optd["ny"] * optd["nz"] / world
     group = int(max(1, min(world, avail * 0.8 // max(per_rank, 1.0))))
     solver = None
     for g0 in range(0, world, group):
         if g0 <= rank < g0 + group:
-            solver, opt, info = build_solver(ma, optd, rank, world, comm, local_rank)
+            solver, opt, info = build_solver(ma, optd, rank, world, comm, local_rank, mesh_path=args.mesh_path)
         barrier()
     n_owned = info["owned_cells"]
     second = bool(optd["second_order_space"])
@@ -402,7 +418,7 @@ def gpu_arm(args):
         for name in ("sod_o2", "flatplate"):
             if name == args.workload:
                 continue
-            s2, _, i2 = build_solver(ma, workload_options(name, 1), 0, 1, None, local_rank)
+            s2, _, i2 = build_solver(ma, workload_options(name, 1), 0, 1, None, local_rank, mesh_path=args.mesh_path)
             t2 = time_steps(s2, max(3, args.steps // 4), 3, barrier)
             v2 = i2["owned_cells"] * t2["steps"] / t2["step_seconds"]
             also[name] = {"value": v2, "unit": "cell-updates/s", "steps": int(t2["steps"]), "cells": i2["owned_cells"],
@@ -436,7 +452,8 @@ def gpu_arm(args):
                            "arith": "fast (FMA contraction, reciprocal multiplication); parity vs the reference in tests/",
                            "l2": "no flush needed: %.1f GB of solver state per GPU >> 126 MB L2" % (t["device_bytes"] / 1e9),
                            "device_bytes": int(t["device_bytes"]), "tiles": int(t["num_tiles"]),
-                           "setup_seconds": {k: round(v, 2) for k, v in info.items() if k.endswith("_seconds")}},
+                           "setup_seconds": {k: round(v, 2) for k, v in info.items() if k.endswith("_seconds")},
+                           "mesh_path": info["mesh_path"]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "wall_ms_per_step": 1e3 * t["wall_seconds"] / args.steps, "result_finite": finite}
         if also:
@@ -457,6 +474,8 @@ def main():
     ap.add_argument("--workload", default="sod_o2_visc", choices=["sod_o2_visc", "sod_o2", "flatplate", "flatplate_strong"])
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="override the GLOBAL mesh (debugging only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--mesh-path", default="structured", choices=["structured", "arrays"],
+                    help="how the solver is constructed (set-up only; the timed steps are the same kernels)")
     ap.add_argument("--no-also", dest="also", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")

@@ -190,6 +190,34 @@ class TimeSolverExplicitRK4:
         _abi.check(self._lib.ma_solver_create(C.byref(cmesh), C.byref(options), C.byref(cfg), C.byref(h)))
         self._handle = h
 
+    @classmethod
+    def from_options(cls, options, rank=0, nranks=1, device=0, arith=ARITH_FAST, tile_dims=(0, 0, 0), block_threads=0,
+                     comm=None, overlap_halo=True, stream=None):
+        """Parallel3DMesh + fillMeshData + the constructor in one call (ma_solver_create_structured): the block's
+        device layout is built straight from (i, j, k) and its geometry is evaluated on the GPU; the same solver,
+        bit for bit, as TimeSolverExplicitRK4(Parallel3DMesh.from_options(options, rank, nranks).fillMeshData(), ...).
+        There is no host mesh afterwards: Solve() cannot write `results.<rank>` (use the mesh constructor for that)."""
+        self = cls.__new__(cls)
+        self._lib = _abi.load()
+        self.options = options
+        self._mesh = self._mesh_keepalive = None
+        cfg = _abi.SolverConfig()
+        self._lib.ma_solver_config_default(C.byref(cfg))
+        cfg.device, cfg.arith = device, arith
+        cfg.tile_dims[0], cfg.tile_dims[1], cfg.tile_dims[2] = tile_dims
+        cfg.block_threads = block_threads
+        cfg.comm = comm._handle if comm is not None else None
+        cfg.overlap_halo = 1 if overlap_halo else 0
+        cfg.stream = stream
+        self._comm = comm
+        h = C.c_void_p()
+        _abi.check(self._lib.ma_solver_create_structured(C.byref(options), rank, nranks, C.byref(cfg), C.byref(h)))
+        self._handle = h
+        owned, ghosts = C.c_int(), C.c_int()
+        _abi.check(self._lib.ma_solver_num_cells(h, C.byref(owned), C.byref(ghosts)))
+        self.num_owned_cells, self.num_ghosts = owned.value, ghosts.value
+        return self
+
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h:

@@ -86,6 +86,9 @@ SYMBOLS = {
     "ma_solver_config_default": (None, [C.POINTER(SolverConfig)]),
     "ma_solver_create": (C.c_int, [C.POINTER(Mesh), C.POINTER(Options), C.POINTER(SolverConfig),
                                    C.POINTER(C.c_void_p)]),
+    "ma_solver_create_structured": (C.c_int, [C.POINTER(Options), C.c_int, C.c_int, C.POINTER(SolverConfig),
+                                              C.POINTER(C.c_void_p)]),
+    "ma_solver_num_cells": (C.c_int, [C.c_void_p, _ip, _ip]),
     "ma_solver_destroy": (None, [C.c_void_p]),
     "ma_solver_initialize": (C.c_int, [C.c_void_p]),
     "ma_solver_step": (C.c_int, [C.c_void_p, C.c_int]),

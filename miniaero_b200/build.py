@@ -71,6 +71,12 @@ def build(force=False, verbose=False):
             if force or _newer(obj, [src] + headers):
                 _run([nvcc] + ARCH + NVCC_COMMON + ["-Xptxas", "-v"] + extra + ["-c", src, "-o", obj], log, verbose)
             objs.append(obj)
+        # device-side mesh geometry: the host generator's expressions, no FMA contraction (same bits as the host)
+        src = os.path.join(CSRC, "geom_kernels.cu")
+        obj = os.path.join(BUILD, "geom_kernels.o")
+        if force or _newer(obj, [src] + headers):
+            _run([nvcc] + ARCH + NVCC_COMMON + ["-Xptxas", "-v", "-fmad=false", "-c", src, "-o", obj], log, verbose)
+        objs.append(obj)
         for name in ("solver.cu",):
             src = os.path.join(CSRC, name)
             obj = os.path.join(BUILD, name.replace(".cu", ".o"))

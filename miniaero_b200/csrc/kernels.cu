@@ -1421,6 +1421,11 @@ cudaError_t launch_grad_limiter(const DevMesh &m, const double *V, double *grad,
 cudaError_t flux_rk_prepare(const DevMesh &m, int smem_bytes) {
   cudaError_t e;
   (void)m;
+  // the attribute belongs to the kernel, not to a solver: keep the largest request of any solver of this process,
+  // so that an earlier, larger-tiled solver can still launch after a later one was created
+  static int high_water = 0;
+  if (smem_bytes > high_water) high_water = smem_bytes;
+  smem_bytes = high_water;
 #define MA_SET(K)                                                                          \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);    \
   if (e != cudaSuccess) return e;

@@ -3,6 +3,8 @@
 #include "layout.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -88,146 +90,364 @@ inline void pack_conflict_free(const std::vector<PackItem> &items, int lane0, st
 
 inline uint64_t morton3(long x, long y, long z) { return spread3((uint64_t)x) << 2 | spread3((uint64_t)y) << 1 | spread3((uint64_t)z); }
 
-}  // namespace
 
-int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tangents, HostLayout &L) {
-  const int n_owned = mesh.num_owned_cells, n_ghost = mesh.num_ghosts;
-  const long n_cells = (long)n_owned + n_ghost;
-  if (n_owned <= 0 || n_ghost < 0) return ma_set_error(MA_ERR_INVALID, "mesh: num_owned_cells must be > 0");
-  if (!mesh.cell_coordinates || !mesh.cell_volumes)
-    return ma_set_error(MA_ERR_INVALID, "mesh: cell_coordinates / cell_volumes are NULL");
-  if (mesh.num_boundary_sets < 0 || mesh.num_boundary_sets > MA_MAX_BC_SETS)
-    return ma_set_error(MA_ERR_INVALID, "mesh: num_boundary_sets out of range");
-  auto faces_ok = [](const ma_faces &f) {
-    return f.nfaces == 0 || (f.nfaces > 0 && f.coordinates && f.face_normal && f.face_tangent && f.face_binormal &&
-                             f.face_cell_conn && f.cell_flux_index);
-  };
-  if (!faces_ok(mesh.internal_faces)) return ma_set_error(MA_ERR_INVALID, "mesh: internal_faces has NULL arrays");
-  for (int b = 0; b < mesh.num_boundary_sets; ++b) {
-    if (!faces_ok(mesh.boundary_faces[b])) return ma_set_error(MA_ERR_INVALID, "mesh: boundary set has NULL arrays");
-    if (mesh.boundary_type[b] < 0 || mesh.boundary_type[b] > 3)
-      return ma_set_error(MA_ERR_INVALID, "mesh: unknown boundary_type");
+// What the builder asks about (owned cell c, slot s)
+struct SlotInfo {
+  int other;       // cell across the face (caller's numbering): -1 boundary face, >= n_owned ghost
+  int bc_type;     // ma_bc_type of a boundary face, -1 otherwise
+  int side;        // 0: c is elem1 (the normal points out of c), 1: c is elem2
+  int other_slot;  // slot of the face in the cell across (interior faces)
+};
+
+// ---- a mesh handed over as reference-format arrays (ma_mesh) ---------------------------------------------
+struct ArrayAccess {
+  const ma_mesh &mesh;
+  int n_owned = 0, n_ghost = 0;
+  long n_cells = 0, n_int = 0;
+  std::vector<long> set_base;
+  std::vector<uint32_t> cf;  // (cell, slot) -> global_face * 2 + side; internal faces first, then the boundary sets
+  double lo[3], h[3];
+  long nbins[3];
+  static constexpr bool kStructured = false;
+
+  explicit ArrayAccess(const ma_mesh &m) : mesh(m) {}
+
+  int prepare() {
+    n_owned = mesh.num_owned_cells, n_ghost = mesh.num_ghosts;
+    n_cells = (long)n_owned + n_ghost;
+    if (n_owned <= 0 || n_ghost < 0) return ma_set_error(MA_ERR_INVALID, "mesh: num_owned_cells must be > 0");
+    if (!mesh.cell_coordinates || !mesh.cell_volumes)
+      return ma_set_error(MA_ERR_INVALID, "mesh: cell_coordinates / cell_volumes are NULL");
+    if (mesh.num_boundary_sets < 0 || mesh.num_boundary_sets > MA_MAX_BC_SETS)
+      return ma_set_error(MA_ERR_INVALID, "mesh: num_boundary_sets out of range");
+    auto faces_ok = [](const ma_faces &f) {
+      return f.nfaces == 0 || (f.nfaces > 0 && f.coordinates && f.face_normal && f.face_tangent && f.face_binormal &&
+                               f.face_cell_conn && f.cell_flux_index);
+    };
+    if (!faces_ok(mesh.internal_faces)) return ma_set_error(MA_ERR_INVALID, "mesh: internal_faces has NULL arrays");
+    for (int b = 0; b < mesh.num_boundary_sets; ++b) {
+      if (!faces_ok(mesh.boundary_faces[b])) return ma_set_error(MA_ERR_INVALID, "mesh: boundary set has NULL arrays");
+      if (mesh.boundary_type[b] < 0 || mesh.boundary_type[b] > 3)
+        return ma_set_error(MA_ERR_INVALID, "mesh: unknown boundary_type");
+    }
+    if (n_ghost > 0 && (mesh.num_ranks < 2 || !mesh.send_count || !mesh.recv_count || !mesh.send_local_ids ||
+                        !mesh.recv_local_ids))
+      return ma_set_error(MA_ERR_INVALID, "mesh: ghosts present but exchange lists are missing");
+
+    // cell -> face table over owned cells
+    n_int = mesh.internal_faces.nfaces;
+    set_base.assign(mesh.num_boundary_sets + 1, n_int);
+    for (int b = 0; b < mesh.num_boundary_sets; ++b) set_base[b + 1] = set_base[b] + mesh.boundary_faces[b].nfaces;
+    const long n_faces_all = set_base[mesh.num_boundary_sets];
+    if (n_faces_all >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "mesh: more than 2^31 faces");
+    const uint32_t kNone = 0xFFFFFFFFu;
+    cf.assign((size_t)n_owned * 6, kNone);
+    int bad = 0;
+    {
+      const int *conn = mesh.internal_faces.face_cell_conn, *slot = mesh.internal_faces.cell_flux_index;
+      const long ncl = n_cells;
+      const int no = n_owned;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+      for (long f = 0; f < n_int; ++f) {
+        for (int side = 0; side < 2; ++side) {
+          const int c = conn[2 * f + side], s = slot[2 * f + side];
+          if (c < 0 || c >= ncl || s < 0 || s > 5) {
+            ++bad;
+            continue;
+          }
+          if (c < no) cf[(size_t)c * 6 + s] = (uint32_t)(f * 2 + side);
+        }
+      }
+      for (int b = 0; b < mesh.num_boundary_sets; ++b) {
+        const ma_faces &F = mesh.boundary_faces[b];
+        const long base = set_base[b];
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+        for (long f = 0; f < F.nfaces; ++f) {
+          const int c = F.face_cell_conn[2 * f], s = F.cell_flux_index[2 * f];
+          if (c < 0 || c >= no || s < 0 || s > 5) {
+            ++bad;
+            continue;
+          }
+          cf[(size_t)c * 6 + s] = (uint32_t)((base + f) * 2);
+        }
+      }
+    }
+    if (bad) return ma_set_error(MA_ERR_INVALID, "mesh: face_cell_conn / cell_flux_index out of range");
+    {
+      long missing = 0;
+#pragma omp parallel for schedule(static) reduction(+ : missing)
+      for (long i = 0; i < (long)n_owned * 6; ++i) missing += (cf[i] == kNone);
+      if (missing)
+        return ma_set_error(MA_ERR_INVALID, "mesh: " + std::to_string(missing) +
+                                                " (cell, slot) pairs of owned cells have no face (hex cells need 6)");
+    }
+    return MA_OK;
   }
-  if (n_ghost > 0 && (mesh.num_ranks < 2 || !mesh.send_count || !mesh.recv_count || !mesh.send_local_ids ||
-                      !mesh.recv_local_ids))
-    return ma_set_error(MA_ERR_INVALID, "mesh: ghosts present but exchange lists are missing");
 
+  struct FaceSrc {  // where a face lives in the caller's arrays
+    const ma_faces *f;
+    long index;
+    int bc_type;  // -1: internal
+  };
+  FaceSrc face_src(uint32_t ref) const {
+    const long g = ref >> 1;
+    FaceSrc s;
+    if (g < n_int) {
+      s.f = &mesh.internal_faces, s.index = g, s.bc_type = -1;
+    } else {
+      int b = 0;
+      while (g >= set_base[b + 1]) ++b;
+      s.f = &mesh.boundary_faces[b], s.index = g - set_base[b], s.bc_type = mesh.boundary_type[b];
+    }
+    return s;
+  }
+  SlotInfo info(int c, int s) const {
+    const uint32_t ref = cf[(size_t)c * 6 + s];
+    const long g = ref >> 1;
+    SlotInfo r;
+    r.side = (int)(ref & 1);
+    if (g >= n_int) {
+      r.other = -1, r.other_slot = -1;
+      r.bc_type = face_src(ref).bc_type;
+    } else {
+      r.other = mesh.internal_faces.face_cell_conn[2 * g + (1 - r.side)];
+      r.other_slot = mesh.internal_faces.cell_flux_index[2 * g + (1 - r.side)];
+      r.bc_type = -1;
+    }
+    return r;
+  }
+  // area vector, tangent, binormal, centroid of the face in slot s of owned cell c
+  void face_geometry(int c, int s, double *n, double *t, double *b, double *x) const {
+    const FaceSrc src = face_src(cf[(size_t)c * 6 + s]);
+    const size_t fi = (size_t)src.index;
+    for (int d = 0; d < 3; ++d) {
+      n[d] = src.f->face_normal[3 * fi + d];
+      t[d] = src.f->face_tangent[3 * fi + d];
+      b[d] = src.f->face_binormal[3 * fi + d];
+      x[d] = src.f->coordinates[3 * fi + d];
+    }
+  }
+  uint32_t face_code(int, int) const { return 0; }
+  void cell_geometry(long c, double *xyz, double *vol) const {
+    for (int d = 0; d < 3; ++d) xyz[d] = mesh.cell_coordinates[3 * c + d];
+    *vol = mesh.cell_volumes[c];
+  }
+
+  // spatial binning of owned cells.  The mean centroid spacing along each axis is taken over internal faces whose
+  // cell-to-cell vector is dominated by that axis; for a structured block this recovers (i,j,k) exactly, for a
+  // general hex mesh it only has to give compact tiles.
+  void prepare_bins() {
+    const double *xc = mesh.cell_coordinates;
+    double hi[3] = {-1e300, -1e300, -1e300};
+    lo[0] = lo[1] = lo[2] = 1e300;
+    for (long c = 0; c < n_owned; ++c)
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = std::min(lo[d], xc[3 * c + d]);
+        hi[d] = std::max(hi[d], xc[3 * c + d]);
+      }
+    double hsum[3] = {0, 0, 0};
+    long hcnt[3] = {0, 0, 0};
+    {
+      const int *conn = mesh.internal_faces.face_cell_conn;
+      double s0 = 0, s1 = 0, s2 = 0;
+      long c0 = 0, c1 = 0, c2 = 0;
+      const int no = n_owned;
+#pragma omp parallel for schedule(static) reduction(+ : s0, s1, s2, c0, c1, c2)
+      for (long f = 0; f < n_int; ++f) {
+        const int l = conn[2 * f], r = conn[2 * f + 1];
+        if (l >= no || r >= no) continue;
+        const double d0 = std::fabs(xc[3 * (long)r] - xc[3 * (long)l]);
+        const double d1 = std::fabs(xc[3 * (long)r + 1] - xc[3 * (long)l + 1]);
+        const double d2 = std::fabs(xc[3 * (long)r + 2] - xc[3 * (long)l + 2]);
+        if (d0 >= d1 && d0 >= d2) {
+          s0 += d0, ++c0;
+        } else if (d1 >= d2) {
+          s1 += d1, ++c1;
+        } else {
+          s2 += d2, ++c2;
+        }
+      }
+      hsum[0] = s0, hsum[1] = s1, hsum[2] = s2;
+      hcnt[0] = c0, hcnt[1] = c1, hcnt[2] = c2;
+    }
+    for (int d = 0; d < 3; ++d) {
+      h[d] = hcnt[d] ? hsum[d] / (double)hcnt[d] : 0.0;
+      if (!(h[d] > 0.0) || !((hi[d] - lo[d]) / h[d] < 1e9)) h[d] = (hi[d] - lo[d]) + 1.0;  // one bin
+      nbins[d] = (long)std::floor((hi[d] - lo[d]) / h[d] + 0.5) + 1;
+    }
+  }
+  void bin(long c, long q[3]) const {
+    const double *xc = mesh.cell_coordinates;
+    for (int d = 0; d < 3; ++d) {
+      q[d] = (long)std::floor((xc[3 * c + d] - lo[d]) / h[d] + 0.5);
+      q[d] = std::max(0L, std::min(q[d], nbins[d] - 1));
+    }
+  }
+  int num_ranks() const { return mesh.num_ranks; }
+  int my_rank() const { return mesh.my_rank; }
+  // exchange lists of peer p: counts, and the i-th send / recv cell (caller's numbering) from running offsets
+  int send_count(int p) const { return mesh.send_count[p]; }
+  int recv_count(int p) const { return mesh.recv_count[p]; }
+  int send_id(long off) const { return mesh.send_local_ids[off]; }
+  int recv_id(long off) const { return mesh.recv_local_ids[off]; }
+};
+
+// ---- one block of the in-code structured mesh, never materialised (mesh_geom.h) ------------------------------
+struct StructuredAccess {
+  GridGen g;
+  GridTables tables;
+  int bc_of_face[6];  // ma_bc_type of the domain side behind local face f (Parallel3DMesh.h:382-396)
+  int n_owned = 0, n_ghost = 0;
+  long n_cells = 0;
+  long nbins[3];
+  std::vector<int> send_ids, recv_ids, send_counts, recv_counts;
+  static constexpr bool kStructured = true;
+
+  int prepare(const ma_options &opt, int rank, int num_ranks) {
+    if (opt.nx <= 0 || opt.ny <= 0 || opt.nz <= 0)
+      return ma_set_error(MA_ERR_INVALID, "structured mesh: nx, ny, nz must be positive");
+    if (num_ranks < 1 || rank < 0 || rank >= num_ranks) return ma_set_error(MA_ERR_INVALID, "structured mesh: bad rank / num_ranks");
+    if (!arrange(g.b, opt.nx, opt.ny, opt.nz, rank, num_ranks))
+      return ma_set_error(MA_ERR_INVALID, "MPI number of ranks must be a power of 2.");  // Parallel3DMesh.C:262-265
+    for (int d = 0; d < 3; ++d)
+      if (g.b.n[d] < 1) return ma_set_error(MA_ERR_INVALID, "structured mesh: more blocks than cells in a direction");
+    const double PI = 3.14159265;  // Parallel3DMesh.h:473
+    tables.build(g, opt.lx, opt.ly, opt.lz, std::tan(opt.angle * PI / 180.0));
+    g.set_block_counts();
+    if ((g.nowned + g.nghost) * 3 > 2000000000L)
+      return ma_set_error(MA_ERR_INVALID, "structured mesh: more than 2^31 faces on one block");
+    n_owned = (int)g.nowned, n_ghost = (int)g.nghost, n_cells = g.nowned + g.nghost;
+    for (int d = 0; d < 3; ++d) nbins[d] = g.b.n[d];
+    const int pt = opt.problem_type;
+    bc_of_face[0] = (pt == 1) ? MA_BC_NOSLIP : MA_BC_TANGENT;       // bottom (-y)
+    bc_of_face[2] = (pt == 1) ? MA_BC_EXTRAPOLATE : MA_BC_TANGENT;  // top (+y)
+    bc_of_face[4] = MA_BC_TANGENT;                                  // front (-z)
+    bc_of_face[5] = MA_BC_TANGENT;                                  // back (+z)
+    bc_of_face[1] = MA_BC_EXTRAPOLATE;                              // right (+x)
+    bc_of_face[3] = (pt == 0) ? MA_BC_EXTRAPOLATE : MA_BC_INFLOW;   // left (-x)
+    // ghost exchange lists: per neighbour rank (ascending), ordered by global id (host_mesh.cpp)
+    send_counts.assign(num_ranks, 0);
+    recv_counts.assign(num_ranks, 0);
+    if (num_ranks > 1) {
+      const Block &b = g.b;
+      struct Nb {
+        int rank, axis, hi;
+      };
+      std::vector<Nb> nbs;
+      for (int d = 0; d < 3; ++d)
+        for (int hi = 0; hi < 2; ++hi) {
+          if (!(hi ? b.ghi[d] : b.glo[d])) continue;
+          int nb_blk[3] = {b.blk[0], b.blk[1], b.blk[2]};
+          nb_blk[d] += hi ? 1 : -1;
+          nbs.push_back({nb_blk[0] + b.np[0] * (nb_blk[1] + b.np[1] * nb_blk[2]), d, hi});
+        }
+      std::sort(nbs.begin(), nbs.end(), [](const Nb &a, const Nb &c) { return a.rank < c.rank; });
+      for (const Nb &nb : nbs) {
+        const int d = nb.axis;
+        const int a1 = (d == 0) ? 1 : 0, a2 = (d == 2) ? 1 : 2;
+        const long cnt = (long)b.n[a1] * b.n[a2];
+        send_counts[nb.rank] = (int)cnt;
+        recv_counts[nb.rank] = (int)cnt;
+        for (long w = 0; w < cnt; ++w) {
+          int idx[3];
+          idx[a1] = (int)(w / b.n[a2]);
+          idx[a2] = (int)(w % b.n[a2]);
+          idx[d] = nb.hi ? b.n[d] - 1 : 0;
+          send_ids.push_back((int)g.cell_id(idx[0], idx[1], idx[2]));
+          idx[d] = nb.hi ? b.n[d] : -1;
+          recv_ids.push_back((int)g.cell_id(idx[0], idx[1], idx[2]));
+        }
+      }
+    }
+    num_ranks_ = num_ranks, my_rank_ = rank;
+    return MA_OK;
+  }
+  int num_ranks_ = 1, my_rank_ = 0;
+
+  SlotInfo info(int c, int s) const {
+    int i, j, k, di, dj, dk;
+    g.cell_ijk(c, i, j, k);
+    face_dir(s, di, dj, dk);
+    const long nb = g.cell_id(i + di, j + dj, k + dk);
+    SlotInfo r;
+    if (nb < 0) {
+      r.other = -1, r.other_slot = -1, r.side = 0, r.bc_type = bc_of_face[s];
+    } else {
+      r.other = (int)nb, r.other_slot = opposite_face(s), r.bc_type = -1;
+      r.side = nb > c ? 0 : 1;  // a face is created by the lower-numbered of its two cells (MeshProcessor.C:54-120)
+    }
+    return r;
+  }
+  // the cell that created the face (elem1) and the local face it created it as: Face.C computes the geometry there
+  void elem1(int c, int s, int &i, int &j, int &k, int &f) const {
+    int di, dj, dk;
+    g.cell_ijk(c, i, j, k);
+    face_dir(s, di, dj, dk);
+    const long nb = g.cell_id(i + di, j + dj, k + dk);
+    f = s;
+    if (nb >= 0 && nb < c) {
+      i += di, j += dj, k += dk;
+      f = opposite_face(s);
+    }
+  }
+  void face_geometry(int c, int s, double *n, double *t, double *b, double *x) const {
+    int i, j, k, f;
+    elem1(c, s, i, j, k, f);
+    g.face_geometry(i, j, k, f, x, n, t, b);
+  }
+  // (elem1 cell in the block-local (i+1, j+1, k+1) lattice) * 8 + elem1 local face: what the device-side geometry
+  // kernel needs to recompute the face (geom_kernels.cu)
+  uint32_t face_code(int c, int s) const {
+    int i, j, k, f;
+    elem1(c, s, i, j, k, f);
+    const long lat = ((long)(i + 1) * (g.b.n[1] + 2) + (j + 1)) * (g.b.n[2] + 2) + (k + 1);
+    return (uint32_t)(lat * 8 + f);
+  }
+  void cell_geometry(long c, double *xyz, double *vol) const {
+    int i, j, k;
+    g.cell_ijk(c, i, j, k);
+    g.cell_geometry(i, j, k, xyz, vol);
+  }
+  void prepare_bins() {}
+  void bin(long c, long q[3]) const {
+    int i, j, k;
+    g.cell_ijk(c, i, j, k);
+    q[0] = i, q[1] = j, q[2] = k;
+  }
+  int num_ranks() const { return num_ranks_; }
+  int my_rank() const { return my_rank_; }
+  int send_count(int p) const { return send_counts[p]; }
+  int recv_count(int p) const { return recv_counts[p]; }
+  int send_id(long off) const { return send_ids[off]; }
+  int recv_id(long off) const { return recv_ids[off]; }
+};
+
+template <class Mesh>
+int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents, bool defer_geometry, HostLayout &L) {
+  const int n_owned = mesh.n_owned, n_ghost = mesh.n_ghost;
+  const long n_cells = mesh.n_cells;
   L = HostLayout();
   L.n_owned = n_owned;
   L.n_ghost = n_ghost;
   L.geom_components = with_tangents ? 12 : 6;
+  L.geometry_deferred = defer_geometry;
   L.stride = round_up(n_cells, 32);
   for (int d = 0; d < 3; ++d) L.tile_dims[d] = tile_dims_in[d] > 0 ? tile_dims_in[d] : 8;
   L.max_tile_cells = L.tile_dims[0] * L.tile_dims[1] * L.tile_dims[2];
   if (L.max_tile_cells > 4096) return ma_set_error(MA_ERR_INVALID, "tile_dims: at most 4096 cells per tile");
 
-  // ---- 1. cell -> face table over owned cells: ref = global_face*2 + side, global face numbering is
-  // internal faces first, then the boundary sets in order.
-  const long n_int = mesh.internal_faces.nfaces;
-  std::vector<long> set_base(mesh.num_boundary_sets + 1, n_int);
-  for (int b = 0; b < mesh.num_boundary_sets; ++b) set_base[b + 1] = set_base[b] + mesh.boundary_faces[b].nfaces;
-  const long n_faces_all = set_base[mesh.num_boundary_sets];
-  if (n_faces_all >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "mesh: more than 2^31 faces");
-  const uint32_t kNone = 0xFFFFFFFFu;
-  std::vector<uint32_t> cf((size_t)n_owned * 6, kNone);
-  int bad = 0;
-  {
-    const int *conn = mesh.internal_faces.face_cell_conn, *slot = mesh.internal_faces.cell_flux_index;
-#pragma omp parallel for schedule(static) reduction(+ : bad)
-    for (long f = 0; f < n_int; ++f) {
-      for (int side = 0; side < 2; ++side) {
-        const int c = conn[2 * f + side], s = slot[2 * f + side];
-        if (c < 0 || c >= n_cells || s < 0 || s > 5) {
-          ++bad;
-          continue;
-        }
-        if (c < n_owned) cf[(size_t)c * 6 + s] = (uint32_t)(f * 2 + side);
-      }
-    }
-    for (int b = 0; b < mesh.num_boundary_sets; ++b) {
-      const ma_faces &F = mesh.boundary_faces[b];
-      const long base = set_base[b];
-#pragma omp parallel for schedule(static) reduction(+ : bad)
-      for (long f = 0; f < F.nfaces; ++f) {
-        const int c = F.face_cell_conn[2 * f], s = F.cell_flux_index[2 * f];
-        if (c < 0 || c >= n_owned || s < 0 || s > 5) {
-          ++bad;
-          continue;
-        }
-        cf[(size_t)c * 6 + s] = (uint32_t)((base + f) * 2);
-      }
-    }
-  }
-  if (bad) return ma_set_error(MA_ERR_INVALID, "mesh: face_cell_conn / cell_flux_index out of range");
-  {
-    long missing = 0;
-#pragma omp parallel for schedule(static) reduction(+ : missing)
-    for (long i = 0; i < (long)n_owned * 6; ++i) missing += (cf[i] == kNone);
-    if (missing)
-      return ma_set_error(MA_ERR_INVALID, "mesh: " + std::to_string(missing) +
-                                              " (cell, slot) pairs of owned cells have no face (hex cells need 6)");
-  }
-  auto face_src = [&](uint32_t ref) {
-    const long g = ref >> 1;
-    FaceSrc s;
-    if (g < n_int) {
-      s.f = &mesh.internal_faces, s.index = (int)g, s.bc_type = -1;
-    } else {
-      int b = 0;
-      while (g >= set_base[b + 1]) ++b;
-      s.f = &mesh.boundary_faces[b], s.index = (int)(g - set_base[b]), s.bc_type = mesh.boundary_type[b];
-    }
-    return s;
+  const bool timing = getenv("MINIAERO_LAYOUT_TIMING") != nullptr;
+  auto tprev = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "layout: %-28s %.3f s\n", what, std::chrono::duration<double>(now - tprev).count());
+    tprev = now;
   };
-  // the cell on the other side of (owned) cell c's face `ref`; -1 for a boundary face
-  auto other_cell = [&](uint32_t ref) -> int {
-    const long g = ref >> 1;
-    if (g >= n_int) return -1;
-    return mesh.internal_faces.face_cell_conn[2 * g + (1 - (int)(ref & 1))];
-  };
-
-  // ---- 2. spatial binning of owned cells.  The mean centroid spacing along each axis is taken over
-  // internal faces whose cell-to-cell vector is dominated by that axis; for a structured block this
-  // recovers (i,j,k) exactly, for a general hex mesh it only has to give compact tiles.
-  const double *xc = mesh.cell_coordinates;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (long c = 0; c < n_owned; ++c)
-    for (int d = 0; d < 3; ++d) {
-      lo[d] = std::min(lo[d], xc[3 * c + d]);
-      hi[d] = std::max(hi[d], xc[3 * c + d]);
-    }
-  double hsum[3] = {0, 0, 0};
-  long hcnt[3] = {0, 0, 0};
-  {
-    const int *conn = mesh.internal_faces.face_cell_conn;
-    double s0 = 0, s1 = 0, s2 = 0;
-    long c0 = 0, c1 = 0, c2 = 0;
-#pragma omp parallel for schedule(static) reduction(+ : s0, s1, s2, c0, c1, c2)
-    for (long f = 0; f < n_int; ++f) {
-      const int l = conn[2 * f], r = conn[2 * f + 1];
-      if (l >= n_owned || r >= n_owned) continue;
-      const double d0 = std::fabs(xc[3 * (long)r] - xc[3 * (long)l]);
-      const double d1 = std::fabs(xc[3 * (long)r + 1] - xc[3 * (long)l + 1]);
-      const double d2 = std::fabs(xc[3 * (long)r + 2] - xc[3 * (long)l + 2]);
-      if (d0 >= d1 && d0 >= d2) {
-        s0 += d0, ++c0;
-      } else if (d1 >= d2) {
-        s1 += d1, ++c1;
-      } else {
-        s2 += d2, ++c2;
-      }
-    }
-    hsum[0] = s0, hsum[1] = s1, hsum[2] = s2;
-    hcnt[0] = c0, hcnt[1] = c1, hcnt[2] = c2;
-  }
-  double h[3];
-  long nbin[3];
-  for (int d = 0; d < 3; ++d) {
-    h[d] = hcnt[d] ? hsum[d] / (double)hcnt[d] : 0.0;
-    if (!(h[d] > 0.0) || !((hi[d] - lo[d]) / h[d] < 1e9)) h[d] = (hi[d] - lo[d]) + 1.0;  // one bin
-    nbin[d] = (long)std::floor((hi[d] - lo[d]) / h[d] + 0.5) + 1;
-  }
-  long ntile_d[3];
+  // ---- 2. spatial binning of owned cells
+  mesh.prepare_bins();
+  long nbin[3], ntile_d[3];
+  for (int d = 0; d < 3; ++d) nbin[d] = mesh.nbins[d];
   for (int d = 0; d < 3; ++d) ntile_d[d] = (nbin[d] + L.tile_dims[d] - 1) / L.tile_dims[d];
 
   const char *order_env = getenv("MINIAERO_TILE_ORDER");  // experiment knob: "linear" = x-major tile order
@@ -244,9 +464,8 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
 #pragma omp parallel for schedule(static)
   for (long c = 0; c < n_owned; ++c) {
     long q[3], t[3], l[3];
+    mesh.bin(c, q);
     for (int d = 0; d < 3; ++d) {
-      q[d] = (long)std::floor((xc[3 * c + d] - lo[d]) / h[d] + 0.5);
-      q[d] = std::max(0L, std::min(q[d], nbin[d] - 1));
       t[d] = q[d] / L.tile_dims[d];
       l[d] = q[d] % L.tile_dims[d];
     }
@@ -274,6 +493,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   std::sort(keys.begin(), keys.end(), key_less);
 #endif
 
+  lap("bin + sort cells");
   // ---- 3. cut tiles, classify (touches a ghost?), order interior tiles first, renumber
   struct RawTile {
     long first;
@@ -296,7 +516,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
       for (long i = raw[t].first; i < raw[t].first + raw[t].count && !bnd; ++i) {
         const int c = keys[i].cell;
         for (int s = 0; s < 6; ++s)
-          if (other_cell(cf[(size_t)c * 6 + s]) >= n_owned) {
+          if (mesh.info(c, s).other >= n_owned) {
             bnd = 1;
             break;
           }
@@ -337,16 +557,22 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   }
   std::vector<Key>().swap(keys);
 
+  lap("tiles + renumbering");
   // ---- 4. cell SoA
-  L.cell_xyz.assign((size_t)3 * L.stride, 0.0);
-  L.cell_vol.assign((size_t)L.stride, 1.0);
+  if (!defer_geometry) {
+    L.cell_xyz.assign((size_t)3 * L.stride, 0.0);
+    L.cell_vol.assign((size_t)L.stride, 1.0);
+  }
 #pragma omp parallel for schedule(static)
-  for (long c = 0; c < n_cells; ++c) {
+  for (long c = 0; c < (defer_geometry ? 0 : n_cells); ++c) {
     const long o = L.new2old[c];
-    for (int d = 0; d < 3; ++d) L.cell_xyz[(size_t)d * L.stride + c] = xc[3 * o + d];
-    L.cell_vol[c] = mesh.cell_volumes[o];
+    double xyz[3], vol;
+    mesh.cell_geometry(o, xyz, &vol);
+    for (int d = 0; d < 3; ++d) L.cell_xyz[(size_t)d * L.stride + c] = xyz[d];
+    L.cell_vol[c] = vol;
   }
 
+  lap("cell geometry");
   // ---- 5. tile face lists.  A face is emitted by its in-tile cell with the larger tile-local index
   // (or by its only in-tile cell), in (cell, slot) order: the flux sweep then walks cells in order
   // and every cell's data is touched within a short window.
@@ -354,7 +580,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.slot_face.assign((size_t)6 * L.slot_stride, 0);
   auto emits = [&](const TileInfo &T, int newc, int s) -> bool {
     const int oldc = L.new2old[newc];
-    const int oth = other_cell(cf[(size_t)oldc * 6 + s]);
+    const int oth = mesh.info(oldc, s).other;
     if (oth < 0 || oth >= n_owned) return true;
     const int on = L.old2new[oth];
     if (on < T.cell_start || on >= T.cell_start + T.cell_count) return true;
@@ -363,7 +589,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   // is the cell on the other side of (new cell c, slot s) outside the tile?  (cut face)
   auto is_cut = [&](const TileInfo &T, int newc, int s) -> bool {
     const int oldc = L.new2old[newc];
-    const int oth = other_cell(cf[(size_t)oldc * 6 + s]);
+    const int oth = mesh.info(oldc, s).other;
     if (oth < 0) return false;
     if (oth >= n_owned) return true;
     const int on = L.old2new[oth];
@@ -408,7 +634,10 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
   L.n_tile_faces = fstart[n_tiles];
   L.n_tile_faces_real = real;
   const size_t NF = (size_t)L.n_tile_faces;
-  L.face_geom.assign((size_t)L.geom_components * NF, 0.0);
+  if (defer_geometry)
+    L.face_code.assign(NF, 0);
+  else
+    L.face_geom.assign((size_t)L.geom_components * NF, 0.0);
   const int GX = with_tangents ? 9 : 3;  // first centroid component
   double frame_err = 0.0;
   L.face_left.assign(NF, 0);
@@ -441,9 +670,9 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
       const bool cut = is_cut(T, c, s);
       group[cut].push_back({c, s});
       if (pack) {
-        const uint32_t ref = cf[(size_t)L.new2old[c] * 6 + s];
-        const int side = (int)(ref & 1), own = shift + (c - T.cell_start);
-        const int oth = other_cell(ref);
+        const SlotInfo si = mesh.info(L.new2old[c], s);
+        const int side = si.side, own = shift + (c - T.cell_start);
+        const int oth = si.other;
         PackItem pi;
         if (cut) {
           pi = {own, -1, side == 0 ? 2 : 3, 0};
@@ -473,46 +702,49 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
       {
         const bool cut = g == 1;
         const int e = (cut ? T.cut_start : 0) + (int)q;
-        const uint32_t ref = cf[(size_t)oldc * 6 + s];
-        const int side = (int)(ref & 1);
-        const FaceSrc src = face_src(ref);
+        const SlotInfo si = mesh.info(oldc, s);
+        const int side = si.side;
         const size_t j = (size_t)T.face_start + e;
-        const size_t fi = (size_t)src.index;
-        const double *fn = src.f->face_normal + 3 * fi, *ft = src.f->face_tangent + 3 * fi,
-                     *fb = src.f->face_binormal + 3 * fi;
-        for (int d = 0; d < 3; ++d) {
-          if (with_tangents) {
-            L.face_geom[(0 + d) * NF + j] = fn[d];
-            L.face_geom[(3 + d) * NF + j] = ft[d];
-            L.face_geom[(6 + d) * NF + j] = fb[d];
-            L.face_geom[(GX + d) * NF + j] = src.f->coordinates[3 * fi + d];
-          } else {
-            const size_t base = (size_t)6 * T.face_start + e;
-            L.face_geom[base + (0 + d) * fcp] = fn[d];
-            L.face_geom[base + (3 + d) * fcp] = src.f->coordinates[3 * fi + d];
+        if (defer_geometry) {
+          L.face_code[j] = mesh.face_code(oldc, s);
+        } else {
+          double fn[3], ft[3], fb[3], fx[3];
+          mesh.face_geometry(oldc, s, fn, ft, fb, fx);
+          for (int d = 0; d < 3; ++d) {
+            if (with_tangents) {
+              L.face_geom[(0 + d) * NF + j] = fn[d];
+              L.face_geom[(3 + d) * NF + j] = ft[d];
+              L.face_geom[(6 + d) * NF + j] = fb[d];
+              L.face_geom[(GX + d) * NF + j] = fx[d];
+            } else {
+              const size_t base = (size_t)6 * T.face_start + e;
+              L.face_geom[base + (0 + d) * fcp] = fn[d];
+              L.face_geom[base + (3 + d) * fcp] = fx[d];
+            }
+          }
+          if (!Mesh::kStructured) {  // how far (n/|n|, t, b/|n|) is from orthonormal (FAST arithmetic relies on it,
+                                     // Face.C:81-96; the in-code mesh builds it that way)
+            const double a2 = fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2];
+            const double an = std::sqrt(a2);
+            const double tt = ft[0] * ft[0] + ft[1] * ft[1] + ft[2] * ft[2];
+            const double bb = (fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]) / a2;
+            const double nt = (fn[0] * ft[0] + fn[1] * ft[1] + fn[2] * ft[2]) / an;
+            const double nb = (fn[0] * fb[0] + fn[1] * fb[1] + fn[2] * fb[2]) / a2;
+            const double tb = (ft[0] * fb[0] + ft[1] * fb[1] + ft[2] * fb[2]) / an;
+            double err = std::max(std::fabs(tt - 1.0), std::fabs(bb - 1.0));
+            err = std::max(err, std::max(std::fabs(nt), std::max(std::fabs(nb), std::fabs(tb))));
+            if (!(err <= frame_err)) frame_err = (err == err) ? err : 1e300;
           }
         }
-        {  // how far (n/|n|, t, b/|n|) is from orthonormal (FAST arithmetic relies on it, Face.C:81-96)
-          const double a2 = fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2];
-          const double an = std::sqrt(a2);
-          const double tt = ft[0] * ft[0] + ft[1] * ft[1] + ft[2] * ft[2];
-          const double bb = (fb[0] * fb[0] + fb[1] * fb[1] + fb[2] * fb[2]) / a2;
-          const double nt = (fn[0] * ft[0] + fn[1] * ft[1] + fn[2] * ft[2]) / an;
-          const double nb = (fn[0] * fb[0] + fn[1] * fb[1] + fn[2] * fb[2]) / a2;
-          const double tb = (ft[0] * fb[0] + ft[1] * fb[1] + ft[2] * fb[2]) / an;
-          double err = std::max(std::fabs(tt - 1.0), std::fabs(bb - 1.0));
-          err = std::max(err, std::max(std::fabs(nt), std::max(std::fabs(nb), std::fabs(tb))));
-          if (!(err <= frame_err)) frame_err = (err == err) ? err : 1e300;
-        }
         const int lc = c - T.cell_start;  // tile-local index of the emitting cell
-        if (src.bc_type >= 0) {
+        if (si.bc_type >= 0) {
           L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (1 << 14) | (side << 15));
           L.face_left[j] = c;
-          L.face_right[j] = bc_code(src.bc_type);
-          L.face_lr[j] = (uint32_t)(shift + lc) | ((uint32_t)(0xFFFF - src.bc_type) << 16);
+          L.face_right[j] = bc_code(si.bc_type);
+          L.face_lr[j] = (uint32_t)(shift + lc) | ((uint32_t)(0xFFFF - si.bc_type) << 16);
         } else {
           L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
-          const int oth_old = src.f->face_cell_conn[2 * fi + (1 - side)];
+          const int oth_old = si.other;
           const int oth_new = L.old2new[oth_old];
           L.face_left[j] = side == 0 ? c : oth_new;
           L.face_right[j] = side == 0 ? oth_new : c;
@@ -522,7 +754,7 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
             L.tile_halo[(size_t)T.halo_start + (e - T.cut_start)] = oth_new;
           } else {
             oth_local = shift + (oth_new - T.cell_start);
-            const int os = src.f->cell_flux_index[2 * fi + (1 - side)];
+            const int os = si.other_slot;
             L.slot_face[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(e | ((1 - side) << 15));
             L.slot_nbr[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(shift + lc);
           }
@@ -536,13 +768,14 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
 
   L.max_frame_error = frame_err;
 
+  lap("tile face lists");
   // ---- 6. halo lists (renumbered), grouped by peer
   if (n_ghost > 0) {
     long so = 0, ro = 0;
-    for (int p = 0; p < mesh.num_ranks; ++p) {
-      const int sc = mesh.send_count[p], rc = mesh.recv_count[p];
+    for (int p = 0; p < mesh.num_ranks(); ++p) {
+      const int sc = mesh.send_count(p), rc = mesh.recv_count(p);
       if (sc < 0 || rc < 0) return ma_set_error(MA_ERR_INVALID, "mesh: negative send/recv count");
-      if (p == mesh.my_rank || (sc == 0 && rc == 0)) {
+      if (p == mesh.my_rank() || (sc == 0 && rc == 0)) {
         so += sc, ro += rc;
         continue;
       }
@@ -550,17 +783,41 @@ int build_layout(const ma_mesh &mesh, const int tile_dims_in[3], bool with_tange
       L.peer_send_count.push_back(sc);
       L.peer_recv_count.push_back(rc);
       for (int i = 0; i < sc; ++i) {
-        const int id = mesh.send_local_ids[so + i];
+        const int id = mesh.send_id(so + i);
         if (id < 0 || id >= n_owned) return ma_set_error(MA_ERR_INVALID, "mesh: send_local_ids out of range");
         L.send_ids.push_back(L.old2new[id]);
       }
       for (int i = 0; i < rc; ++i) {
-        const int id = mesh.recv_local_ids[ro + i];
+        const int id = mesh.recv_id(ro + i);
         if (id < n_owned || id >= n_cells) return ma_set_error(MA_ERR_INVALID, "mesh: recv_local_ids must be ghosts");
         L.recv_ids.push_back(L.old2new[id]);
       }
       so += sc, ro += rc;
     }
+  }
+  return MA_OK;
+}
+
+}  // namespace
+
+int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L) {
+  ArrayAccess a(mesh);
+  int rc = a.prepare();
+  if (rc) return rc;
+  return build_layout_impl(a, tile_dims, with_tangents, false, L);
+}
+
+int build_layout_structured(const ma_options &opt, int rank, int num_ranks, const int tile_dims[3], bool with_tangents,
+                            bool defer_geometry, HostLayout &L, StructuredGrid *grid) {
+  StructuredAccess a;
+  int rc = a.prepare(opt, rank, num_ranks);
+  if (rc) return rc;
+  rc = build_layout_impl(a, tile_dims, with_tangents, defer_geometry, L);
+  if (rc) return rc;
+  if (grid) {
+    grid->gen = a.g;
+    grid->tables = std::move(a.tables);
+    grid->gen.xs = grid->tables.xs.data(), grid->gen.ys = grid->tables.ys.data(), grid->gen.zs = grid->tables.zs.data();
   }
   return MA_OK;
 }

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "mesh_geom.h"
 #include "miniaero_b200.h"
 
 namespace ma {
@@ -59,6 +60,11 @@ struct HostLayout {
   int geom_components = 12;
   double max_frame_error = 0.0;  // worst deviation of (n^, t, b/|a|) from an orthonormal frame over all faces
   std::vector<double> face_geom;
+  // structured path with device-side geometry (build_layout_structured, defer_geometry): face_geom, cell_xyz and
+  // cell_vol stay empty; face_code[j] = (elem1 cell in the block's (n+2)^3 lattice) * 8 + elem1 local face says which
+  // face tile face j is, and new2old which cell, for geom_kernels.cu to evaluate mesh_geom.h on the device
+  bool geometry_deferred = false;
+  std::vector<uint32_t> face_code;
   std::vector<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
   // tile-local connectivity: low 16 bits = left cell, high 16 bits = right cell, as POSITIONS in the tile's staged
   // cell list: own cell lc sits at (cell_start & 1) + lc (the staging copy starts at the even cell below
@@ -78,5 +84,16 @@ struct HostLayout {
 
 // Returns MA_OK or sets the error text.  tile_dims: requested cells per tile per direction.
 int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L);
+
+// The same layout for one block of the in-code structured mesh (the reference's Parallel3DMesh / MeshProcessor,
+// Parallel3DMesh.h:173-449) WITHOUT materialising the reference-format arrays: connectivity, numbering and exchange
+// lists follow from (i, j, k) (mesh_geom.h).  Bit for bit the layout build_layout() makes of ma_mesh_generate()'s
+// mesh (tests/test_layout.py).  defer_geometry: leave face / cell geometry to the device (see HostLayout).
+struct StructuredGrid {
+  GridGen gen;
+  GridTables tables;
+};
+int build_layout_structured(const ma_options &opt, int rank, int num_ranks, const int tile_dims[3], bool with_tangents,
+                            bool defer_geometry, HostLayout &L, StructuredGrid *grid);
 
 }  // namespace ma

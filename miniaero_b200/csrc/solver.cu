@@ -17,6 +17,7 @@
 
 #include "comm.h"
 #include "host_common.h"
+#include "geom_kernels.h"
 #include "kernels.h"
 #include "layout.h"
 #include "miniaero_b200.h"
@@ -397,29 +398,38 @@ void ma_solver_destroy(ma_solver *S) {
   delete S;
 }
 
-int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver_config *cfg_in, ma_solver **out) {
-  if (!mesh || !opt || !out) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: null argument");
-  *out = nullptr;
-  ma_solver_config cfg;
+// common front end of the two constructors: configuration checks and the tile size
+static int create_prologue(const ma_options *opt, const ma_solver_config *cfg_in, ma_solver_config &cfg, int td[3]) {
   if (cfg_in)
     cfg = *cfg_in;
   else
     ma_solver_config_default(&cfg);
   if (cfg.arith != MA_ARITH_FAST && cfg.arith != MA_ARITH_STRICT)
     return ma_set_error(MA_ERR_INVALID, "ma_solver_create: arith must be MA_ARITH_FAST or MA_ARITH_STRICT");
-  if (mesh->num_ghosts > 0 && !cfg.comm)
-    return ma_set_error(MA_ERR_INVALID, "ma_solver_create: mesh has ghost cells but no communicator was given");
   if (!(opt->dt > 0.0)) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: dt must be positive");
   int rc = check_device(cfg.device);
   if (rc) return rc;
-
-  // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 8x4x4 for the FAST staged kernels, whose
-  // shared-memory footprint (28 doubles per own cell + 6 per face + 11 RK operands) leaves room for three CTAs per SM;
+  // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 4x4x8 for the FAST staged kernels, whose
+  // shared-memory footprint (28 doubles per own cell + 6 per face) leaves room for four CTAs per SM;
   // z is the fastest cell index inside a tile, so the long z edge makes the cut-face gathers along x and y contiguous
   const int td_default[2][3] = {{4, 4, 8}, {8, 8, 8}};
-  int td[3];
   for (int d = 0; d < 3; ++d)
     td[d] = cfg.tile_dims[d] > 0 ? cfg.tile_dims[d] : td_default[cfg.arith == MA_ARITH_STRICT ? 1 : 0][d];
+  return MA_OK;
+}
+
+static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid, const ma_options *opt,
+                              const ma_solver_config &cfg, ma_solver **out);
+
+int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver_config *cfg_in, ma_solver **out) {
+  if (!mesh || !opt || !out) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: null argument");
+  *out = nullptr;
+  ma_solver_config cfg;
+  int td[3];
+  int rc = create_prologue(opt, cfg_in, cfg, td);
+  if (rc) return rc;
+  if (mesh->num_ghosts > 0 && !cfg.comm)
+    return ma_set_error(MA_ERR_INVALID, "ma_solver_create: mesh has ghost cells but no communicator was given");
   ma::HostLayout L;
   rc = ma::build_layout(*mesh, td, cfg.arith == MA_ARITH_STRICT, L);
   if (rc) return rc;
@@ -427,8 +437,32 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
     return ma_set_error(MA_ERR_INVALID,
                         "MA_ARITH_FAST needs face (normal, tangent, binormal) triples that are orthogonal with unit tangent and "
                         "|binormal| = |normal| (as Face.C:81-96 builds them); use MA_ARITH_STRICT for arbitrary frames");
-  if (rc) return rc;
+  return solver_from_layout(L, nullptr, opt, cfg, out);
+}
 
+int ma_solver_create_structured(const ma_options *opt, int rank, int num_ranks, const ma_solver_config *cfg_in,
+                                ma_solver **out) {
+  if (!opt || !out) return ma_set_error(MA_ERR_INVALID, "ma_solver_create_structured: null argument");
+  *out = nullptr;
+  ma_solver_config cfg;
+  int td[3];
+  int rc = create_prologue(opt, cfg_in, cfg, td);
+  if (rc) return rc;
+  if (num_ranks > 1 && !cfg.comm)
+    return ma_set_error(MA_ERR_INVALID, "ma_solver_create_structured: more than one rank but no communicator was given");
+  // MINIAERO_HOST_GEOMETRY=1 (debugging): evaluate the geometry on the host and upload it, as ma_solver_create does
+  const char *hg = getenv("MINIAERO_HOST_GEOMETRY");
+  const bool defer = !(hg && hg[0] == '1');
+  ma::HostLayout L;
+  ma::StructuredGrid grid;
+  rc = ma::build_layout_structured(*opt, rank, num_ranks, td, cfg.arith == MA_ARITH_STRICT, defer, L, &grid);
+  if (rc) return rc;
+  return solver_from_layout(L, &grid, opt, cfg, out);
+}
+
+static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid, const ma_options *opt,
+                              const ma_solver_config &cfg, ma_solver **out) {
+  int rc = MA_OK;
   ma_solver *S = new ma_solver();
   std::memset(&S->tm, 0, sizeof(S->tm));
   std::memset(&S->dm, 0, sizeof(S->dm));
@@ -488,10 +522,47 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
                   L.tiles[i].cut_start, L.tiles[i].halo_start};
     MA_TRY(dev_upload(&S->d_tiles, tiles, &S->device_bytes));
   }
-  MA_TRY(dev_upload(&S->d_xyz, L.cell_xyz, &S->device_bytes));
-  MA_TRY(dev_upload(&S->d_vol, L.cell_vol, &S->device_bytes));
-  MA_TRY(dev_upload(&S->d_geom, L.face_geom, &S->device_bytes));
-  std::vector<double>().swap(L.face_geom);
+  if (L.geometry_deferred) {
+    // structured path: face and cell geometry are evaluated on the device (geom_kernels.cu) from the node tables,
+    // the per-face codes and the cell permutation; the temporaries go away afterwards
+    if (!grid) {
+      ma_solver_destroy(S);
+      return ma_set_error(MA_ERR_INVALID, "deferred geometry without a structured grid");
+    }
+    MA_TRY(dev_alloc(&S->d_xyz, (size_t)3 * L.stride, &S->device_bytes));
+    MA_TRY(dev_alloc(&S->d_vol, (size_t)L.stride, &S->device_bytes));
+    MA_TRY(dev_alloc(&S->d_geom, (size_t)L.geom_components * L.n_tile_faces, &S->device_bytes));
+    double *d_xs = nullptr, *d_ys = nullptr, *d_zs = nullptr;
+    uint32_t *d_code = nullptr;
+    int *d_new2old = nullptr;
+    size_t scratch = 0;
+    int r2 = dev_upload(&d_xs, grid->tables.xs, &scratch);
+    if (!r2) r2 = dev_upload(&d_ys, grid->tables.ys, &scratch);
+    if (!r2) r2 = dev_upload(&d_zs, grid->tables.zs, &scratch);
+    if (!r2) r2 = dev_upload(&d_code, L.face_code, &scratch);
+    if (!r2) r2 = dev_upload(&d_new2old, L.new2old, &scratch);
+    cudaError_t ge = cudaSuccess;
+    if (!r2) {
+      ma::GridGen g = grid->gen;
+      g.xs = d_xs, g.ys = d_ys, g.zs = d_zs;
+      ge = ma::launch_device_geometry(g, S->d_tiles, L.n_tiles, d_code, S->d_geom, L.n_tile_faces, L.geom_components,
+                                      d_new2old, (long)L.n_owned + L.n_ghost, L.stride, S->d_xyz, S->d_vol, S->st);
+      if (ge == cudaSuccess) ge = cudaStreamSynchronize(S->st);
+    }
+    for (void *p : {(void *)d_xs, (void *)d_ys, (void *)d_zs, (void *)d_code, (void *)d_new2old})
+      if (p) cudaFree(p);
+    if (r2) {
+      ma_solver_destroy(S);
+      return r2;
+    }
+    MA_CU(ge);
+    std::vector<uint32_t>().swap(L.face_code);
+  } else {
+    MA_TRY(dev_upload(&S->d_xyz, L.cell_xyz, &S->device_bytes));
+    MA_TRY(dev_upload(&S->d_vol, L.cell_vol, &S->device_bytes));
+    MA_TRY(dev_upload(&S->d_geom, L.face_geom, &S->device_bytes));
+    std::vector<double>().swap(L.face_geom);
+  }
   MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
   if (!S->strict) MA_TRY(dev_upload(&S->d_slot_nbr, L.slot_nbr, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
@@ -573,6 +644,13 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
 #undef MA_TRY
 #undef MA_CU
   *out = S;
+  return MA_OK;
+}
+
+int ma_solver_num_cells(const ma_solver *S, int *owned, int *ghosts) {
+  if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
+  if (owned) *owned = S->n_owned;
+  if (ghosts) *ghosts = S->n_ghost;
   return MA_OK;
 }
 

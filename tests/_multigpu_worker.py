@@ -55,6 +55,16 @@ def main():
                     summary["linf_vs_single_domain"] = parity.combine_parts([r["parts_vs_single_domain"] for r in rows])[0]
                 report["%s/arith%d/overlap%d/step%d" % (name, arith, int(overlap), n)] = [summary]
                 del solver
+        # the structured constructor (block layout from (i, j, k), geometry evaluated on the device): same bits
+        opt = ma.Options(**cases.opts_kwargs(dict(inp, ntimesteps=2)))
+        solver = ma.TimeSolverExplicitRK4.from_options(opt, rank, world, device=local, arith=ma.ARITH_STRICT, comm=comm)
+        solver.initialize()
+        solver.step(2)
+        ulp = parity.max_ulp(solver.solution(), g["r%d_step2" % rank])
+        rows = [None] * world
+        dist.all_gather_object(rows, ulp)
+        report["%s/structured/arith1/step2" % name] = [{"ulp": max(rows)}]
+        del solver
         # the reference's own parallel integration test: results.<rank> vs results.<rank>.gold
         if ("r%d_gold" % rank) in g:
             import refrun

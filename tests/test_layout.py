@@ -49,3 +49,25 @@ def test_default_order_is_bank_friendly(checker):
     assert ratio < 1.25, out
     plain = _run(checker, (64, 32, 32), {"MINIAERO_FACE_ORDER": "slot", "MINIAERO_CELL_SWIZZLE": "0"})
     assert float(re.search(r"phase 1 record-read wavefronts / ideal: ([0-9.]+)", plain).group(1)) > ratio
+
+
+@pytest.fixture(scope="module")
+def comparer(tmp_path_factory):
+    from miniaero_b200 import build as b
+    b.build()
+    exe = str(tmp_path_factory.mktemp("layout") / "layout_compare")
+    objs = [os.path.join(b.BUILD, n) for n in ("layout.o", "host_mesh.o", "host_common.o")]
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + b.CSRC, os.path.join(ROOT, "tools", "layout_compare.cpp")] + objs + ["-o", exe], check=True)
+    return exe
+
+
+# NX NY NZ PROBLEM_TYPE ANGLE RANK NRANKS [tile] [strict]
+@pytest.mark.parametrize("args", [(37, 21, 13, 0, 0, 0, 1), (16, 32, 2, 1, 0, 0, 1), (64, 32, 2, 2, 30, 0, 1),
+                                  (32, 16, 8, 2, 30, 1, 4), (32, 64, 2, 1, 0, 5, 8), (13, 7, 5, 2, 17, 0, 1, 3, 5, 2),
+                                  (24, 16, 16, 0, 0, 1, 2, 8, 8, 8, 1), (64, 8, 8, 0, 0, 1, 2), (128, 4, 4, 0, 0, 3, 4)])
+def test_structured_layout_is_the_array_layout(comparer, args):
+    """build_layout_structured() (layout from (i, j, k), nothing materialised) == build_layout(ma_mesh_generate()),
+    every array bit for bit, and the deferred-geometry face codes re-evaluate to the same geometry."""
+    p = subprocess.run([comparer] + [str(a) for a in args], capture_output=True, text=True)
+    assert p.returncode == 0 and "differences: 0" in p.stdout, p.stdout + p.stderr

@@ -14,10 +14,14 @@ def run(nx, ny, nz, second, visc, ptype=0, steps=5, tile=(0, 0, 0), bt=0, lx=0.3
     opt = ma.Options(problem_type=ptype, lx=lx, ly=ly, lz=lz, angle=0.0, nx=nx, ny=ny, nz=nz, ntimesteps=steps, dt=dt,
                      second_order_space=second, viscous=visc)
     t = time.time()
-    mesh = ma.Parallel3DMesh.from_options(opt).fillMeshData()
-    tm = time.time() - t
-    t = time.time()
-    s = ma.TimeSolverExplicitRK4(mesh, opt, tile_dims=tile, block_threads=bt)
+    if os.environ.get('MINIAERO_MESH_PATH', 'structured') == 'structured':   # layout from (i,j,k), geometry on the device
+        tm = 0.0
+        s = ma.TimeSolverExplicitRK4.from_options(opt, tile_dims=tile, block_threads=bt)
+    else:
+        mesh = ma.Parallel3DMesh.from_options(opt).fillMeshData()
+        tm = time.time() - t
+        t = time.time()
+        s = ma.TimeSolverExplicitRK4(mesh, opt, tile_dims=tile, block_threads=bt)
     tl = time.time() - t
     s.initialize()
     s.step(2)
