@@ -113,6 +113,10 @@ const int *ma_mesh_global_ids(const ma_mesh_storage *m);
 /* block decomposition of this rank: nproc[3], block[3], local n[3], offset[3] (Parallel3DMesh.C:247-303) */
 void ma_mesh_decomposition(const ma_mesh_storage *m, int nproc[3], int block[3], int nlocal[3], int offset[3]);
 void ma_mesh_free(ma_mesh_storage *m);
+/* The block decomposition alone (Parallel3DMesh.C:247-303: 2^k ranks, bisect the largest remaining dimension):
+ * blocks per direction, this rank's block coordinates, its local cell counts and global offsets. */
+int ma_block_decomposition(const ma_options *opt, int rank, int num_ranks, int nproc[3], int block[3], int nlocal[3],
+                           int offset[3]);
 
 /* ---- Halo communicator (NCCL send/recv over NVLink) — replaces MPI_COMM_WORLD as used by
  * communicate_ghosted_cell_data, CopyGhost.C:41-79.  One process per GPU; rank 0 obtains the id

@@ -80,6 +80,7 @@ SYMBOLS = {
     "ma_mesh_global_ids": (_ip, [C.c_void_p]),
     "ma_mesh_decomposition": (None, [C.c_void_p, _ip, _ip, _ip, _ip]),
     "ma_mesh_free": (None, [C.c_void_p]),
+    "ma_block_decomposition": (C.c_int, [C.POINTER(Options), C.c_int, C.c_int, _ip, _ip, _ip, _ip]),
     "ma_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "ma_comm_create": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ma_comm_destroy": (None, [C.c_void_p]),

@@ -314,6 +314,22 @@ void ma_mesh_decomposition(const ma_mesh_storage *m, int nproc[3], int block[3],
 }
 void ma_mesh_free(ma_mesh_storage *m) { delete m; }
 
+int ma_block_decomposition(const ma_options *opt, int rank, int num_ranks, int nproc[3], int block[3], int nlocal[3],
+                           int offset[3]) {
+  if (!opt || num_ranks < 1 || rank < 0 || rank >= num_ranks)
+    return ma_set_error(MA_ERR_INVALID, "ma_block_decomposition: bad argument");
+  Block b;
+  if (!arrange(b, opt->nx, opt->ny, opt->nz, rank, num_ranks))
+    return ma_set_error(MA_ERR_INVALID, "MPI number of ranks must be a power of 2.");  // Parallel3DMesh.C:262-265
+  for (int d = 0; d < 3; ++d) {
+    if (nproc) nproc[d] = b.np[d];
+    if (block) block[d] = b.blk[d];
+    if (nlocal) nlocal[d] = b.n[d];
+    if (offset) offset[d] = b.off[d];
+  }
+  return MA_OK;
+}
+
 int ma_write_results(const char *path, const ma_mesh *mesh, const double *solution, int precision) {
   // TimeSolverExplicitRK4.h:514-538
   if (!path || !mesh || !solution) return ma_set_error(MA_ERR_INVALID, "ma_write_results: null argument");

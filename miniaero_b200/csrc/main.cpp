@@ -101,17 +101,15 @@ int main(int argc, char **argv) {
   ma_options opt;
   if (ma_options_read(input.c_str(), &opt)) die("reading the options file");  // Main.C:73-74
 
-  // ---- setup: mesh on the host (Main.C:96-129)
+  // ---- setup (Main.C:96-129).  The reference-format host mesh is only needed to write results.<rank>; without
+  // output the block's layout is built straight from (i, j, k) and its geometry on the device
+  // (ma_solver_create_structured): the solver constructor below is then the whole set-up.
   const auto t_setup = Clock::now();
   ma_mesh_storage *mesh = nullptr;
-  if (ma_mesh_generate(&opt, my_id, num_procs, &mesh)) die("mesh generation");
   int nproc[3], block[3], nlocal[3], offset[3];
-  ma_mesh_decomposition(mesh, nproc, block, nlocal, offset);
-  const double setup_s = seconds_since(t_setup);
-  if (my_id == 0) fprintf(stdout, "\n ... Setup time: %8.2f seconds ...\n", setup_s);
-
-  // ---- run on the device (Main.C:131-150)
-  const auto t_run = Clock::now();
+  if (ma_block_decomposition(&opt, my_id, num_procs, nproc, block, nlocal, offset)) die("block decomposition");
+  if (opt.output_results && ma_mesh_generate(&opt, my_id, num_procs, &mesh)) die("mesh generation");
+  // ---- communicator and solver (the device layout is part of the set-up)
   ma_comm *comm = nullptr;
   if (num_procs > 1) {
     unsigned char id[MA_COMM_ID_BYTES];
@@ -128,13 +126,21 @@ int main(int argc, char **argv) {
   cfg.comm = comm;
   for (int d = 0; d < 3; ++d) cfg.tile_dims[d] = tile[d];
   ma_solver *solver = nullptr;
-  if (ma_solver_create(ma_mesh_view(mesh), &opt, &cfg, &solver)) die("solver");
+  if (mesh ? ma_solver_create(ma_mesh_view(mesh), &opt, &cfg, &solver)
+           : ma_solver_create_structured(&opt, my_id, num_procs, &cfg, &solver))
+    die("solver");
+  const double setup_s = seconds_since(t_setup);
+  if (my_id == 0) fprintf(stdout, "\n ... Setup time: %8.2f seconds ...\n", setup_s);
+  int owned_cells = 0;
+  ma_solver_num_cells(solver, &owned_cells, nullptr);
+  // ---- run on the device (Main.C:131-150)
+  const auto t_run = Clock::now();
   if (ma_solver_solve(solver)) die("Solve");  // prints the progress lines and "Device Run time"
   ma_timing tm;
   ma_solver_get_timing(solver, &tm);
   if (my_id == 0)
     fprintf(stdout, " ... %lld cells x %lld steps: %.4e cell-updates/s on this rank (device time %.3f s) ...\n",
-            (long long)ma_mesh_view(mesh)->num_owned_cells, tm.steps,
+            (long long)owned_cells, tm.steps,
             tm.step_seconds > 0 ? (double)tm.cell_updates / tm.step_seconds : 0.0, tm.step_seconds);
 
   if (opt.output_results) {  // TimeSolverExplicitRK4.h:514-538
@@ -165,7 +171,7 @@ int main(int argc, char **argv) {
   }
   ma_solver_destroy(solver);
   if (comm) ma_comm_destroy(comm);
-  ma_mesh_free(mesh);
+  if (mesh) ma_mesh_free(mesh);
   if (my_id == 0) fprintf(stdout, "\n ... Total elapsed time: %8.2f seconds ...\n", seconds_since(t_start));  // Main.C:90-92
   return 0;
 }

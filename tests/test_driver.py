@@ -20,7 +20,7 @@ def _write_inp(path, inp):
     o = cases.opts_kwargs(inp)
     path.write_text("%d\n%r %r %r %r\n%d %d %d\n%d\n%r\n%d\n%d\n%d\n%d\n" % (
         o["problem_type"], o["lx"], o["ly"], o["lz"], o["angle"], o["nx"], o["ny"], o["nz"], o["ntimesteps"], o["dt"],
-        1, 100, o["second_order_space"], o["viscous"]))
+        o.get("output_results", 1), 100, o["second_order_space"], o["viscous"]))
 
 
 def test_yaml_report_grammar(lib, tmp_path):
@@ -87,3 +87,16 @@ def test_driver_reproduces_the_reference_gold_file(lib, tmp_path, name):
         assert res.shape == gold.shape
         assert refrun.numeric_text_diff(res, gold, rel_tol, floor) == 0
         assert len([f for f in os.listdir(d) if f.endswith(".yaml")]) == 1
+
+
+@pytest.mark.gpu
+def test_driver_without_output_uses_the_structured_constructor(lib, tmp_path):
+    """output_results = 0: no host mesh is generated (ma_solver_create_structured); the run, its progress lines and the
+    YAML report are the same."""
+    inp = dict(cases.EXTRA["sod_o2_visc"], ntimesteps=3, output_results=0)
+    _write_inp(tmp_path / "miniaero.inp", inp)
+    p = subprocess.run([EXE], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "Device Run time" in p.stdout and "Setup time" in p.stdout and "4096 cells x 3 steps" in p.stdout
+    assert not os.path.exists(tmp_path / "results.0")
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".yaml")]) == 1
