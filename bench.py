@@ -263,6 +263,11 @@ def time_steps(solver, steps, warmup, barrier):
 
 
 def gpu_arm(args):
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the one-time host side of the solver construction (tile
+    # topology, OpenMP) would then run single-threaded.  Give each rank its share of the cores — before libgomp loads.
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    if local_world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_cores() // local_world))
     import torch
     import torch.distributed as dist
     import miniaero_b200 as ma
