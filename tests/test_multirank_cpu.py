@@ -58,3 +58,22 @@ def test_processor_arrangement_matches_the_reference_rule(lib):
         assert tuple(md.nproc) == ref_rule(n, r), (n, r, md.nproc)
         bx, by, bz = md.block
         assert r - 1 == bx + md.nproc[0] * (by + md.nproc[1] * bz)
+
+
+def test_block_decomposition_entry_point_matches_the_mesh(lib):
+    """ma_block_decomposition (what the structured constructor and the host driver use) == the decomposition
+    ma_mesh_generate reports, for every rank of several arrangements; and the reference's error for non-2^k ranks."""
+    import ctypes as C
+    import miniaero_b200 as ma
+    from miniaero_b200 import _abi
+    for n, r in [((16, 8, 8), 1), ((16, 8, 8), 2), ((12, 12, 6), 4), ((8, 8, 8), 8), ((32, 4, 2), 4)]:
+        opt = ma.Options(nx=n[0], ny=n[1], nz=n[2])
+        for rank in range(r):
+            md = ma.Parallel3DMesh.from_options(opt, rank, r).fillMeshData()
+            a = [(C.c_int * 3)() for _ in range(4)]
+            _abi.check(lib.ma_block_decomposition(C.byref(opt), rank, r, *a))
+            assert [tuple(x) for x in a] == [tuple(md.nproc), tuple(md.block), tuple(md.nlocal), tuple(md.offset)]
+    opt = ma.Options(nx=8, ny=8, nz=8)
+    a = [(C.c_int * 3)() for _ in range(4)]
+    assert lib.ma_block_decomposition(C.byref(opt), 0, 3, *a) != 0
+    assert b"power of 2" in lib.ma_last_error()
