@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MA_ABI_VERSION 1
+#define MA_ABI_VERSION 2
 #define MA_MAX_BC_SETS 16
 
 typedef enum ma_status {
@@ -137,6 +137,13 @@ typedef enum ma_arith {
                          comparable with the reference's -DCELL_FLUX build */
 } ma_arith;
 
+typedef enum ma_limiter {
+  MA_LIMITER_VENKAT = 0,    /* VenkatLimiter.h:45-73 — what StencilLimiter.h:455,459 call */
+  MA_LIMITER_VANALBADA = 1  /* VanAlbadaLimiter.h:45-65 — shipped by the reference (Flux.h:36) but never called; a
+                               maintainer switches by editing those two call sites.  Functional, not tuned: the
+                               gradient/limiter sweep runs through the gather kernels */
+} ma_limiter;
+
 typedef struct ma_solver_config {
   int device;       /* CUDA device ordinal */
   int arith;        /* ma_arith */
@@ -145,6 +152,7 @@ typedef struct ma_solver_config {
   ma_comm *comm;    /* NULL for a single-domain run; required when mesh->num_ghosts > 0 */
   int overlap_halo; /* non-zero: run interior tiles while the halo exchange is in flight */
   void *stream;     /* cudaStream_t to run on; NULL = a stream owned by the solver */
+  int limiter;      /* ma_limiter (second-order runs) */
 } ma_solver_config;
 void ma_solver_config_default(ma_solver_config *cfg);
 

@@ -21,7 +21,7 @@ import numpy as np
 
 from . import _abi
 from ._abi import (ARITH_FAST, ARITH_STRICT, BC_EXTRAPOLATE, BC_INFLOW, BC_NAMES, BC_NOSLIP, BC_TANGENT,
-                   FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_PRIMITIVES, MiniAeroError)
+                   FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_PRIMITIVES, LIMITER_VENKAT, LIMITER_VANALBADA, MiniAeroError)
 
 __all__ = ["Options", "Parallel3DMesh", "MeshData", "Faces", "TimeSolverExplicitRK4", "HaloComm", "MiniAeroError",
            "ARITH_FAST", "ARITH_STRICT", "probe_roe_flux", "probe_viscous_flux", "probe_primitives",
@@ -171,7 +171,7 @@ class TimeSolverExplicitRK4:
     is in the caller's cell order."""
 
     def __init__(self, input_mesh_data, options, device=0, arith=ARITH_FAST, tile_dims=(0, 0, 0), block_threads=0,
-                 comm=None, overlap_halo=True, stream=None):
+                 comm=None, overlap_halo=True, stream=None, limiter=0):
         self._lib = _abi.load()
         self.options = options
         cmesh, self._mesh_keepalive = _as_c_mesh(input_mesh_data)
@@ -185,6 +185,7 @@ class TimeSolverExplicitRK4:
         cfg.comm = comm._handle if comm is not None else None
         cfg.overlap_halo = 1 if overlap_halo else 0
         cfg.stream = stream
+        cfg.limiter = limiter
         self._comm = comm
         h = C.c_void_p()
         _abi.check(self._lib.ma_solver_create(C.byref(cmesh), C.byref(options), C.byref(cfg), C.byref(h)))
@@ -192,7 +193,7 @@ class TimeSolverExplicitRK4:
 
     @classmethod
     def from_options(cls, options, rank=0, nranks=1, device=0, arith=ARITH_FAST, tile_dims=(0, 0, 0), block_threads=0,
-                     comm=None, overlap_halo=True, stream=None):
+                     comm=None, overlap_halo=True, stream=None, limiter=0):
         """Parallel3DMesh + fillMeshData + the constructor in one call (ma_solver_create_structured): the block's
         device layout is built straight from (i, j, k) and its geometry is evaluated on the GPU; the same solver,
         bit for bit, as TimeSolverExplicitRK4(Parallel3DMesh.from_options(options, rank, nranks).fillMeshData(), ...).
@@ -209,6 +210,7 @@ class TimeSolverExplicitRK4:
         cfg.comm = comm._handle if comm is not None else None
         cfg.overlap_halo = 1 if overlap_halo else 0
         cfg.stream = stream
+        cfg.limiter = limiter
         self._comm = comm
         h = C.c_void_p()
         _abi.check(self._lib.ma_solver_create_structured(C.byref(options), rank, nranks, C.byref(cfg), C.byref(h)))

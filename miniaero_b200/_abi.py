@@ -14,6 +14,7 @@ BC_EXTRAPOLATE, BC_TANGENT, BC_INFLOW, BC_NOSLIP = 0, 1, 2, 3
 BC_NAMES = {"Extrapolate": BC_EXTRAPOLATE, "Tangent": BC_TANGENT, "Inflow": BC_INFLOW, "NoSlip": BC_NOSLIP}
 ARITH_FAST, ARITH_STRICT = 0, 1
 FIELD_GRADIENT, FIELD_LIMITER, FIELD_STAGE_PRIMITIVES = 0, 1, 2
+LIMITER_VENKAT, LIMITER_VANALBADA = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -45,7 +46,7 @@ class Mesh(C.Structure):
 
 class SolverConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("arith", C.c_int), ("tile_dims", C.c_int * 3), ("block_threads", C.c_int),
-                ("comm", C.c_void_p), ("overlap_halo", C.c_int), ("stream", C.c_void_p)]
+                ("comm", C.c_void_p), ("overlap_halo", C.c_int), ("stream", C.c_void_p), ("limiter", C.c_int)]
 
 
 class Timing(C.Structure):

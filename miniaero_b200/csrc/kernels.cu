@@ -215,6 +215,28 @@ __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_ke
         ndumin[k] = V[k] - mn[k];
       }
 #endif
+      if (m.limiter == 1) {
+        // VanAlbadaLimiter.h:45-65 in place of VenkatLimiter at StencilLimiter.h:455,459 (the alternative the reference
+        // ships but never calls): phi = min over the six faces, from 1 (StencilLimiter.h:308-311, 345-346)
+        double pva[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+#pragma unroll
+        for (int s = 0; s < 6; ++s) {
+          const int e = fj[s];
+          double disp[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) disp[d] = __ldg(tg.base + (size_t)(MA_GEOM_XF + d) * tg.cs + e) - xc[d];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            double dU = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) dU += disp[d] * g[k][d];
+            pva[k] = fmin(pva[k], vanalbada_limit(mx[k] - V[k], mn[k] - V[k], dU));
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = pva[k];
+        continue;
+      }
 #pragma unroll
       for (int s = 0; s < 6; ++s) {
         const int e = fj[s];

@@ -1,6 +1,6 @@
 // Host driver: the reference's Main.C shape (Main.C:53-152) on top of the C ABI.
 //
-//   miniaero [--input FILE] [--arith fast|strict] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]
+//   miniaero [--input FILE] [--arith fast|strict] [--limiter venkat|vanalbada] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]
 //
 // reads ./miniaero.inp (Options.h:86), generates this rank's block of the hex mesh on the host, hands it to the
 // solver (the drop-in for TimeSolverExplicitRK4 at Main.C:139-141), optionally writes results.<rank>
@@ -72,7 +72,7 @@ bool exchange_id(int rank, unsigned char id[MA_COMM_ID_BYTES]) {
 int main(int argc, char **argv) {
   const auto t_start = Clock::now();
   std::string input = "miniaero.inp", yaml_dir = ".";
-  int arith = MA_ARITH_FAST, precision = 0, tile[3] = {0, 0, 0};
+  int arith = MA_ARITH_FAST, precision = 0, tile[3] = {0, 0, 0}, limiter = MA_LIMITER_VENKAT;
   bool yaml = true;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -85,12 +85,13 @@ int main(int argc, char **argv) {
     };
     if (a == "--input") input = next();
     else if (a == "--arith") arith = !strcmp(next(), "strict") ? MA_ARITH_STRICT : MA_ARITH_FAST;
+    else if (a == "--limiter") limiter = !strcmp(next(), "vanalbada") ? MA_LIMITER_VANALBADA : MA_LIMITER_VENKAT;
     else if (a == "--tile") sscanf(next(), "%d,%d,%d", &tile[0], &tile[1], &tile[2]);
     else if (a == "--precision") precision = atoi(next());
     else if (a == "--yaml") yaml_dir = next();
     else if (a == "--no-yaml") yaml = false;
     else {
-      fprintf(stderr, "usage: miniaero [--input FILE] [--arith fast|strict] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]\n");
+      fprintf(stderr, "usage: miniaero [--input FILE] [--arith fast|strict] [--limiter venkat|vanalbada] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]\n");
       return a == "--help" || a == "-h" ? 0 : 2;
     }
   }
@@ -123,6 +124,7 @@ int main(int argc, char **argv) {
   ma_solver_config_default(&cfg);
   cfg.device = device;
   cfg.arith = arith;
+  cfg.limiter = limiter;
   cfg.comm = comm;
   for (int d = 0; d < 3; ++d) cfg.tile_dims[d] = tile[d];
   ma_solver *solver = nullptr;

@@ -363,6 +363,7 @@ void ma_solver_config_default(ma_solver_config *cfg) {
   cfg->comm = nullptr;
   cfg->overlap_halo = 1;
   cfg->stream = nullptr;
+  cfg->limiter = MA_LIMITER_VENKAT;
 }
 
 void ma_solver_destroy(ma_solver *S) {
@@ -407,6 +408,8 @@ static int create_prologue(const ma_options *opt, const ma_solver_config *cfg_in
   if (cfg.arith != MA_ARITH_FAST && cfg.arith != MA_ARITH_STRICT)
     return ma_set_error(MA_ERR_INVALID, "ma_solver_create: arith must be MA_ARITH_FAST or MA_ARITH_STRICT");
   if (!(opt->dt > 0.0)) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: dt must be positive");
+  if (cfg.limiter != MA_LIMITER_VENKAT && cfg.limiter != MA_LIMITER_VANALBADA)
+    return ma_set_error(MA_ERR_INVALID, "ma_solver_create: limiter must be MA_LIMITER_VENKAT or MA_LIMITER_VANALBADA");
   int rc = check_device(cfg.device);
   if (rc) return rc;
   // default tile: 8x8x8 cells for the STRICT kernels (flux staging only), 4x4x8 for the FAST staged kernels, whose
@@ -607,7 +610,9 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
      // Experiment knobs: MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma
     const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
     m.tile_class = S->strict ? -1 : ma_fast::pick_tile_class(m.max_tile_cells, m.max_tile_faces, m.max_tile_halo);
-    m.grad_variant = (m.tile_class >= 0 && !(gv && !strcmp(gv, "gather"))) ? 1 : 0;
+    m.limiter = cfg.limiter;
+    // the alternative limiter lives in the gather kernels only (the staged kernel's limiter algebra is Venkatakrishnan's)
+    m.grad_variant = (m.tile_class >= 0 && !(gv && !strcmp(gv, "gather")) && cfg.limiter == MA_LIMITER_VENKAT) ? 1 : 0;
     m.flux_variant = (m.tile_class >= 0 && !(fv && !strcmp(fv, "gather"))) ? 1 : 0;
   }
   m.slot_nbr = S->d_slot_nbr;

@@ -10,6 +10,7 @@
 #   miniAero.atomics     -DATOMICS_FLUX   serial    : the reference Makefile's default build (noise floor)
 #   miniAero.atomics.omp -DATOMICS_FLUX   -fopenmp
 #   miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 over oracle/mpi_standin (N cooperating processes)
+#   miniAero.cell.vanalbada  -DCELL_FLUX with the stencil limiter redirected to VanAlbadaLimiter (oracle/vanalbada_swap.h)
 #   unit_oracle          oracle/unit_oracle.cpp: the reference's device functions (Roe, viscous, primitives, limiters)
 #                        included from the reference headers and evaluated on arrays of inputs
 set -euo pipefail
@@ -26,7 +27,7 @@ SRCS="Main.C Parallel3DMesh.C MeshProcessor.C Face.C Cell.C ElementTopo.C Elemen
 COMMON="-O3 -std=gnu++17 -w -ffp-contract=off -I$HERE/kokkos_standin -I$REF"
 build() { # name, flags
   local name="$1"; shift
-  if [ "$OUT/$name" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] && [ "$OUT/$name" -nt "$HERE/build_ref.sh" ] && [ "$OUT/$name" -nt "$HERE/mpi_standin/mpi.h" ]; then return; fi
+  if [ "$OUT/$name" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] && [ "$OUT/$name" -nt "$HERE/build_ref.sh" ] && [ "$OUT/$name" -nt "$HERE/mpi_standin/mpi.h" ] && [ "$OUT/$name" -nt "$HERE/vanalbada_swap.h" ]; then return; fi
   (cd "$REF" && g++ $COMMON "$@" $SRCS -o "$OUT/$name")
   echo "built $OUT/$name"
 }
@@ -37,6 +38,17 @@ build miniAero.atomics.omp -DATOMICS_FLUX -fopenmp
 # the reference's WITH_MPI path (block decomposition + ghost exchange) over the file-based MPI stand-in:
 # full-precision per-rank results for the multi-GPU parity tests
 build miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 -I$HERE/mpi_standin
+# the limiter the reference ships but never calls
+# (only Main.C — the translation unit that instantiates the solver — sees the redirect; ElementTopoHexa8.C uses the
+# host-side, non-template MathTools of MathTools.h, which must not meet MathToolsDevice.h)
+VA="$OUT/miniAero.cell.vanalbada"
+if [ ! "$VA" -nt "$HERE/vanalbada_swap.h" ] || [ ! "$VA" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] || [ ! "$VA" -nt "$HERE/build_ref.sh" ]; then
+  TMPO="$(mktemp -d)"
+  (cd "$REF" && g++ $COMMON -DCELL_FLUX -include "$HERE/vanalbada_swap.h" -c Main.C -o "$TMPO/Main.o" &&
+   g++ $COMMON -DCELL_FLUX "$TMPO/Main.o" ${SRCS#Main.C } -o "$VA")
+  rm -rf "$TMPO"
+  echo "built $VA"
+fi
 # unit oracle: a driver of ours around the reference's headers (no reference source is copied)
 if [ ! "$OUT/unit_oracle" -nt "$HERE/unit_oracle.cpp" ] || [ ! "$OUT/unit_oracle" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ]; then
   g++ $COMMON -DCELL_FLUX "$HERE/unit_oracle.cpp" -o "$OUT/unit_oracle"

@@ -146,3 +146,13 @@ def test_fullsize_column_golden_comes_from_this_oracle():
     scale = np.abs(sol).max(axis=(0, 1, 2))
     scale[1:4] = np.sqrt((sol[..., 1:4] ** 2).sum(axis=-1)).max()
     assert (spread <= 1e-14 * scale).all()
+
+
+@pytest.mark.parametrize("name", ["sod_o2", "ramp_odd"])
+def test_vanalbada_golden_vectors_come_from_the_redirected_reference(name):
+    """tests/golden/vanalbada_*.npz = the unmodified reference sources with the stencil limiter class redirected to
+    VanAlbadaLimiter (oracle/vanalbada_swap.h); a different scheme from the Venkatakrishnan default after a step."""
+    g = parity.golden("vanalbada_" + name)
+    out = refrun.run_reference(dict(cases.EXTRA[name], ntimesteps=2), kind="cell.vanalbada")
+    assert parity.max_ulp(refrun.solution_from_dumps(out["dumps"]), g["cell_step2"]) == 0
+    assert parity.max_ulp(g["cell_step2"], parity.golden(name)["cell_step2"]) != 0
