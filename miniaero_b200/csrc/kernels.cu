@@ -577,7 +577,10 @@ using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
 #define MA_C128_GB1 4
 #endif
 using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 8x4x4 / 4x4x8 bricks (flux: 12 warps per SM, 168 registers, no spills)
-using Cap256 = TileCap<256, 896, 256, 256, 1, 2, 256, 1>;  // 8x8x4 bricks
+#ifndef MA_C256_FB
+#define MA_C256_FB 1
+#endif
+using Cap256 = TileCap<256, 896, 256, 256, 1, 2, 256, MA_C256_FB>;  // 8x8x4 / 4x8x8 bricks
 
 // ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
 // One own cell: neighbours (sV), face normals and centroids (sG) from shared memory; sn[s] = slot_face | slot_nbr << 16

@@ -28,6 +28,7 @@ VARIANTS = {
     "p592h": ["-DMA_FLUX_PREFETCH_AHEAD=592", "-DMA_HEADER_AHEAD=1536"],
     "p592g": ["-DMA_FLUX_PREFETCH_AHEAD=592", "-DMA_HEADER_AHEAD=1536", "-DMA_FLUX_PREFETCH_MIN_BYTES=2048"],
     "h1024": ["-DMA_HEADER_AHEAD=1024"],
+    "c256b2": ["-DMA_C256_FB=2"],
     "t128b3p": ["-DMA_FLUX_PREFETCH_AHEAD=444"] + OLD,
     "g5": ["-DMA_C128_GB1=5"],
     "x_copyonly": ["-DMA_FLUX_EXPERIMENT=1"],

@@ -66,6 +66,7 @@ if __name__ == '__main__':
         run(256, 128, 64, 1, 1, ptype=1, lx=2.0, ly=0.008, lz=1.0, dt=3e-8, tag='flatplate')
     elif mode == 'one':  # python tools/quickbench.py one NX NY NZ [tag]
         nx, ny, nz = (int(x) for x in sys.argv[2:5])
-        run(nx, ny, nz, 1, 1, tag=sys.argv[5] if len(sys.argv) > 5 else '')
+        tile = tuple(int(x) for x in os.environ.get('MINIAERO_TILE', '0,0,0').split(','))
+        run(nx, ny, nz, 1, 1, tile=tile, tag=sys.argv[5] if len(sys.argv) > 5 else '')
     elif mode == 'big':
         run(512, 512, 256, 1, 1, tag='sod_o2_visc 67M')
