@@ -568,8 +568,20 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   }
   MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
   if (!S->strict) MA_TRY(dev_upload(&S->d_slot_nbr, L.slot_nbr, &S->device_bytes));
-  MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
-  MA_TRY(dev_upload(&S->d_fr, L.face_right, &S->device_bytes));
+  // kernel variants (FAST: the bulk-copy staged tile kernels when a capacity class holds every tile, else the gather
+  // kernels; experiment knobs MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma).  The alternative limiter
+  // lives in the gather kernels only (the staged kernel's limiter algebra is Venkatakrishnan's).
+  const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
+  const int tile_class = S->strict ? -1 : ma_fast::pick_tile_class(L.max_tile_cells_real, L.max_tile_faces, L.max_tile_halo);
+  const int grad_variant =
+      (tile_class >= 0 && !(gv && !strcmp(gv, "gather")) && cfg.limiter == MA_LIMITER_VENKAT) ? 1 : 0;
+  const int flux_variant = (tile_class >= 0 && !(fv && !strcmp(fv, "gather"))) ? 1 : 0;
+  // the global face -> cell lists are read by the gather kernels only (the staged kernels use the 16-bit tile-local
+  // connectivity): 29 bytes per cell that the default FAST configuration does not spend
+  if (S->strict || grad_variant == 0 || flux_variant == 0) {
+    MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
+    MA_TRY(dev_upload(&S->d_fr, L.face_right, &S->device_bytes));
+  }
   MA_TRY(dev_upload(&S->d_face_lr, L.face_lr, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_tile_halo, L.tile_halo, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_old2new, L.old2new, &S->device_bytes));
@@ -606,15 +618,10 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   m.max_tile_cells = L.max_tile_cells_real, m.max_tile_faces = L.max_tile_faces;
   m.max_tile_halo = L.max_tile_halo, m.max_tile_local = L.max_tile_local;
   m.halo_stride = L.halo_stride;
-  {  // FAST: the bulk-copy staged tile kernels when a capacity class holds every tile, else the gather kernels.
-     // Experiment knobs: MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma
-    const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
-    m.tile_class = S->strict ? -1 : ma_fast::pick_tile_class(m.max_tile_cells, m.max_tile_faces, m.max_tile_halo);
-    m.limiter = cfg.limiter;
-    // the alternative limiter lives in the gather kernels only (the staged kernel's limiter algebra is Venkatakrishnan's)
-    m.grad_variant = (m.tile_class >= 0 && !(gv && !strcmp(gv, "gather")) && cfg.limiter == MA_LIMITER_VENKAT) ? 1 : 0;
-    m.flux_variant = (m.tile_class >= 0 && !(fv && !strcmp(fv, "gather"))) ? 1 : 0;
-  }
+  m.limiter = cfg.limiter;
+  m.tile_class = tile_class;
+  m.grad_variant = grad_variant;
+  m.flux_variant = flux_variant;
   m.slot_nbr = S->d_slot_nbr;
   m.face_lr = S->d_face_lr;
   m.tile_halo = S->d_tile_halo;

@@ -156,3 +156,10 @@ def test_vanalbada_golden_vectors_come_from_the_redirected_reference(name):
     out = refrun.run_reference(dict(cases.EXTRA[name], ntimesteps=2), kind="cell.vanalbada")
     assert parity.max_ulp(refrun.solution_from_dumps(out["dumps"]), g["cell_step2"]) == 0
     assert parity.max_ulp(g["cell_step2"], parity.golden(name)["cell_step2"]) != 0
+
+
+def test_initial_condition_golden_comes_from_this_oracle():
+    g = parity.golden("initial_conditions")
+    for name in g.files:
+        out = refrun.run_reference(dict(cases.EXTRA[name], ntimesteps=0), kind="cell")
+        assert parity.max_ulp(refrun.solution_from_dumps(out["dumps"]), g[name]) == 0
