@@ -213,14 +213,14 @@ def reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def build_solver(ma, optd, rank, world, comm, local_rank, keep_mesh=False, mesh_path="structured"):
+def build_solver(ma, optd, rank, world, comm, local_rank, keep_mesh=False, mesh_path="structured", arith=0):
     """mesh_path "structured": ma_solver_create_structured (layout from (i, j, k), geometry evaluated on the device);
     "arrays": ma_mesh_generate + ma_solver_create (the reference-format arrays, re-packed and uploaded).  Same solver,
     bit for bit (tests/test_gpu_structured.py)."""
     opt = ma.Options(ntimesteps=1, output_results=0, output_frequency=10 ** 9, **optd)
     t0 = time.perf_counter()
     if mesh_path == "structured" and not keep_mesh:
-        solver = ma.TimeSolverExplicitRK4.from_options(opt, rank, world, device=local_rank, comm=comm)
+        solver = ma.TimeSolverExplicitRK4.from_options(opt, rank, world, device=local_rank, comm=comm, arith=arith)
         t2 = time.perf_counter()
         n = [optd["nx"], optd["ny"], optd["nz"]]
         nproc, left = [1, 1, 1], world
@@ -234,7 +234,7 @@ def build_solver(ma, optd, rank, world, comm, local_rank, keep_mesh=False, mesh_
         return solver, opt, info
     mesh = ma.Parallel3DMesh.from_options(opt, rank, world).fillMeshData()
     t1 = time.perf_counter()
-    solver = ma.TimeSolverExplicitRK4(mesh, opt, device=local_rank, comm=comm)
+    solver = ma.TimeSolverExplicitRK4(mesh, opt, device=local_rank, comm=comm, arith=arith)
     t2 = time.perf_counter()
     info = {"mesh_seconds": t1 - t0, "layout_upload_seconds": t2 - t1, "owned_cells": mesh.num_owned_cells,
             "ghost_cells": mesh.num_ghosts, "nlocal": list(mesh.nlocal), "nproc": list(mesh.nproc), "mesh_path": "arrays"}
@@ -430,6 +430,18 @@ def gpu_arm(args):
                           "ms_per_step": 1e3 * t2["step_seconds"] / t2["steps"],
                           "whole_step_roofline_frac": BYTES_PER_CELL_UPDATE_O2 * v2 / 1e9 / peak}
             del s2
+        # the bit-for-bit mode (MA_ARITH_STRICT: IEEE evaluation in the reference's order, no FMA, gather kernels), the
+        # default workload on a quarter-size mesh: what exact reproduction of the reference's -DCELL_FLUX build costs
+        if args.workload == "sod_o2_visc":
+            o3 = workload_options("sod_o2_visc", 1, (512, 256, 128))
+            s3, _, i3 = build_solver(ma, o3, 0, 1, None, local_rank, mesh_path=args.mesh_path, arith=ma.ARITH_STRICT)
+            t3 = time_steps(s3, 3, 3, barrier)
+            v3 = i3["owned_cells"] * t3["steps"] / t3["step_seconds"]
+            also["sod_o2_visc_strict_arith"] = {"value": v3, "unit": "cell-updates/s", "steps": int(t3["steps"]),
+                                                "cells": i3["owned_cells"],
+                                                "ms_per_step": 1e3 * t3["step_seconds"] / t3["steps"],
+                                                "what": "MA_ARITH_STRICT: bit for bit the reference's -DCELL_FLUX results"}
+            del s3
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:

@@ -125,6 +125,12 @@ struct ma_solver {
   ma_timing tm;
   double sim_time = 0.0;
   long time_it = 0;
+  // one RK4 step (4 stages, 8 launches) captured as a CUDA graph: single-domain runs without per-kernel profiling
+  // replay it, so a step costs one launch on the host (the reference's own test meshes are launch-bound on a B200).
+  // Indexed by the parity of vcur at the start of the step (a step flips it four times).
+  cudaGraphExec_t step_graph[2] = {nullptr, nullptr};
+  long long step_graph_launches = 0;  // kernel launches one replay stands for
+  bool use_graph = true;
   // ma_solver_submit pipeline: two upload and two download staging buffers, one copy stream per direction
   struct Pipe {
     cudaStream_t cin = nullptr, cout = nullptr;
@@ -319,6 +325,51 @@ int run_stage(ma_solver *S, const Api &K, int k) {
   return start_state_exchange(S, Vnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
 }
 
+// One RK4 time step on the solver's stream (TimeSolverExplicitRK4.h:340-491).  Single-domain runs replay a CUDA graph
+// of the four stages (captured on first use); runs with a halo exchange (NCCL on a second stream) or with per-kernel
+// profiling events launch the stages directly.
+int one_step(ma_solver *S, const Api &K) {
+  S->sim_time += S->opt.dt;  // TimeSolverExplicitRK4.h:343
+  S->time_it++;
+  const bool graph_ok = S->use_graph && S->n_ghost == 0 && !S->profiling && !S->u_pending;
+  if (!graph_ok) {
+    for (int k = 0; k < 4; ++k) {
+      int rc = run_stage(S, K, k);
+      if (rc) return rc;
+    }
+    return MA_OK;
+  }
+  const int par = S->vcur;
+  if (!S->step_graph[par]) {
+    const long long before = S->tm.kernel_launches;
+    cudaGraph_t g = nullptr;
+    MA_CUDA_TRY(cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal));
+    int rc = MA_OK;
+    for (int k = 0; k < 4 && !rc; ++k) rc = run_stage(S, K, k);
+    const cudaError_t ce = cudaStreamEndCapture(S->st, &g);
+    S->step_graph_launches = S->tm.kernel_launches - before;
+    S->tm.kernel_launches = before;
+    if (rc || ce != cudaSuccess || !g) {  // capture not possible here: fall back to direct launches for good
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      S->use_graph = false;
+      if (rc) return rc;
+      for (int k = 0; k < 4; ++k) {
+        rc = run_stage(S, K, k);
+        if (rc) return rc;
+      }
+      return MA_OK;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&S->step_graph[par], g, 0);
+    cudaGraphDestroy(g);
+    MA_CUDA_TRY(ie);
+  }
+  MA_CUDA_TRY(cudaGraphLaunch(S->step_graph[par], S->st));
+  S->tm.kernel_launches += S->step_graph_launches;
+  S->last_stage_prims = S->d_V[par ^ 1];  // stage 3 reads the buffer stage 2 wrote
+  return MA_OK;
+}
+
 int ensure_staging(ma_solver *S, size_t elems) {
   if (S->stage_elems >= elems) return MA_OK;
   if (S->d_stage) {
@@ -385,6 +436,8 @@ void ma_solver_destroy(ma_solver *S) {
   }
   if (S->pipe.cin) cudaStreamSynchronize(S->pipe.cin);
   if (S->pipe.cout) cudaStreamSynchronize(S->pipe.cout);
+  for (int i = 0; i < 2; ++i)
+    if (S->step_graph[i]) cudaGraphExecDestroy(S->step_graph[i]);
   for (int i = 0; i < 2; ++i) {
     if (S->pipe.d_in[i]) cudaFree(S->pipe.d_in[i]);
     if (S->pipe.d_out[i]) cudaFree(S->pipe.d_out[i]);
@@ -482,6 +535,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   S->peer_rank = L.peer_rank, S->peer_send = L.peer_send_count, S->peer_recv = L.peer_recv_count;
   S->n_send = (int)L.send_ids.size(), S->n_recv = (int)L.recv_ids.size();
   if (cfg.block_threads > 0) S->flux_threads = S->grad_threads = std::min(256, (cfg.block_threads + 31) / 32 * 32);
+  if (const char *ge = getenv("MINIAERO_CUDA_GRAPH")) S->use_graph = ge[0] != '0';  // experiment knob
 
 #define MA_TRY(expr)        \
   do {                      \
@@ -691,12 +745,8 @@ int ma_solver_step(ma_solver *S, int nsteps) {
   const Api K = api_of(S->strict);
   MA_CUDA_TRY(cudaEventRecord(S->ev_t0, S->st));
   for (int it = 0; it < nsteps; ++it) {
-    S->sim_time += S->opt.dt;  // TimeSolverExplicitRK4.h:343
-    S->time_it++;
-    for (int k = 0; k < 4; ++k) {
-      int rc = run_stage(S, K, k);
-      if (rc) return rc;
-    }
+    int rc = one_step(S, K);
+    if (rc) return rc;
   }
   int rc = wait_state_exchange(S);  // the timed region ends with the ghosts of the new solution in place
   if (rc) return rc;
@@ -793,12 +843,8 @@ int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, in
   rc = start_state_exchange(S, S->d_V[S->vcur]);
   if (rc) return rc;
   for (int it = 0; it < nsteps; ++it) {
-    S->sim_time += S->opt.dt;
-    S->time_it++;
-    for (int k = 0; k < 4; ++k) {
-      rc = run_stage(S, K, k);
-      if (rc) return rc;
-    }
+    rc = one_step(S, K);
+    if (rc) return rc;
   }
   rc = wait_state_exchange(S);
   if (rc) return rc;
