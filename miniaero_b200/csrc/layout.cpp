@@ -3,6 +3,9 @@
 #include "layout.h"
 
 #include <algorithm>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <chrono>
 #include <cstdio>
 #include <cmath>
@@ -228,6 +231,7 @@ struct ArrayAccess {
     }
   }
   uint32_t face_code(int, int) const { return 0; }
+  uint64_t tile_key(int, const int *, int, int) const { return 0; }
   void cell_geometry(long c, double *xyz, double *vol) const {
     for (int d = 0; d < 3; ++d) xyz[d] = mesh.cell_coordinates[3 * c + d];
     *vol = mesh.cell_volumes[c];
@@ -414,6 +418,26 @@ struct StructuredAccess {
     g.cell_ijk(c, i, j, k);
     q[0] = i, q[1] = j, q[2] = k;
   }
+  // Everything the face list of a tile depends on, for a tile that is a brick of the block: its extents, what lies
+  // behind each of its six sides (another tile of the block / a ghost layer / the domain boundary) and the parity of
+  // its first cell (the staged positions are shifted by it).  Tiles with equal keys have the same tile-local face
+  // order, so the builder computes it once per key (a few dozen keys per block).  0 = not a brick: no sharing.
+  uint64_t tile_key(int first_cell, const int td[3], int cell_count, int parity) const {
+    int ijk[3];
+    g.cell_ijk(first_cell, ijk[0], ijk[1], ijk[2]);
+    uint64_t key = 1;
+    long cells = 1;
+    for (int d = 0; d < 3; ++d) {
+      const int origin = ijk[d] / td[d] * td[d];
+      const int ext = std::min(td[d], g.b.n[d] - origin);
+      cells *= ext;
+      const int lo = origin > 0 ? 0 : (g.b.glo[d] ? 1 : 2);
+      const int hi = origin + ext < g.b.n[d] ? 0 : (g.b.ghi[d] ? 1 : 2);
+      key = key << 16 | (uint64_t)(ext & 0xfff) << 4 | (uint64_t)(lo << 2 | hi);
+    }
+    if (cells != cell_count) return 0;
+    return key << 1 | (uint64_t)(parity & 1);
+  }
   int num_ranks() const { return num_ranks_; }
   int my_rank() const { return my_rank_; }
   int send_count(int p) const { return send_counts[p]; }
@@ -595,18 +619,91 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     const int on = L.old2new[oth];
     return on < T.cell_start || on >= T.cell_start + T.cell_count;
   };
+  const char *fo_env = getenv("MINIAERO_FACE_ORDER");
+  const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
+  const bool pack = !by_cell && !(fo_env && !strcmp(fo_env, "slot"));
+  // The tile-local face order: closed / boundary faces first, cut faces last.  Inside each group the faces are listed
+  // by slot (direction), then by cell — consecutive faces read consecutive own cells and consecutive neighbours — and,
+  // for the staged FAST kernels, that list is re-packed half-warp by half-warp so that the 16 lanes of a shared-memory
+  // wavefront read 16 different banks (pack_conflict_free; MINIAERO_FACE_ORDER=slot keeps the plain list).
+  // MINIAERO_FACE_ORDER=cell (and STRICT) keeps (cell, slot) order (the gather kernels' L1 locality).
+  struct TileOrder {  // (tile-local cell, slot) of every tile face, in order; group 0 closed / boundary, 1 cut
+    std::vector<uint16_t> lc[2];
+    std::vector<uint8_t> slot[2];
+  };
+  auto compute_order = [&](const TileInfo &T, TileOrder &O) {
+    const int shift = T.cell_start & 1;
+    struct Emit {
+      int c, s;
+    };
+    std::vector<Emit> group[2];
+    std::vector<PackItem> pitems[2];
+    for (int it = 0; it < 6 * T.cell_count; ++it) {
+      const int c = T.cell_start + (by_cell ? it / 6 : it % T.cell_count);
+      const int s = by_cell ? it % 6 : it / T.cell_count;
+      if (!emits(T, c, s)) continue;
+      const bool cut = is_cut(T, c, s);
+      group[cut].push_back({c, s});
+      if (pack) {
+        const SlotInfo si = mesh.info(L.new2old[c], s);
+        const int side = si.side, own = shift + (c - T.cell_start);
+        const int oth = si.other;
+        PackItem pi;
+        if (cut) {
+          pi = {own, -1, side == 0 ? 2 : 3, 0};
+        } else if (oth < 0) {
+          pi = {own, -1, 2, 0};
+        } else {
+          const int op = shift + (L.old2new[oth] - T.cell_start);
+          pi = side == 0 ? PackItem{own, op, 0, 1} : PackItem{op, own, 0, 1};
+        }
+        pitems[cut].push_back(pi);
+      }
+    }
+    std::vector<int> porder;
+    for (int g = 0; g < 2; ++g) {
+      if (pack) {
+        // the closed group follows the cut group in the kernel's work-item numbering
+        pack_conflict_free(pitems[g], g == 0 ? (int)(group[1].size() & 15) : 0, porder);
+      } else {
+        porder.resize(group[g].size());
+        for (size_t i = 0; i < group[g].size(); ++i) porder[i] = (int)i;
+      }
+      O.lc[g].resize(group[g].size());
+      O.slot[g].resize(group[g].size());
+      for (size_t q = 0; q < group[g].size(); ++q) {
+        O.lc[g][q] = (uint16_t)(group[g][porder[q]].c - T.cell_start);
+        O.slot[g][q] = (uint8_t)group[g][porder[q]].s;
+      }
+    }
+  };
+  // structured blocks: tiles with the same key (StructuredAccess::tile_key) share one order
+  std::unordered_map<uint64_t, std::shared_ptr<const TileOrder>> order_cache;
+  std::mutex order_mutex;
+  auto order_of = [&](const TileInfo &T) -> std::shared_ptr<const TileOrder> {
+    uint64_t key = 0;
+    if (Mesh::kStructured && L.max_tile_cells < 4096)
+      key = mesh.tile_key(L.new2old[T.cell_start], L.tile_dims, T.cell_count, T.cell_start & 1);
+    if (key) {
+      std::lock_guard<std::mutex> lock(order_mutex);
+      auto it = order_cache.find(key);
+      if (it != order_cache.end()) return it->second;
+    }
+    auto O = std::make_shared<TileOrder>();
+    compute_order(T, *O);
+    if (key) {
+      std::lock_guard<std::mutex> lock(order_mutex);
+      order_cache.emplace(key, O);
+    }
+    return O;
+  };
   std::vector<long> fstart(n_tiles + 1, 0), hstart(n_tiles + 1, 0);
   int max_faces = 0, max_local = 0, max_halo = 0;
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : max_faces, max_local, max_halo)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
-    int cnt = 0, cut = 0;
-    for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c)
-      for (int s = 0; s < 6; ++s) {
-        if (!emits(T, c, s)) continue;
-        ++cnt;
-        cut += is_cut(T, c, s) ? 1 : 0;
-      }
+    const std::shared_ptr<const TileOrder> O = order_of(T);
+    const int cut = (int)O->lc[1].size(), cnt = cut + (int)O->lc[0].size();
     L.tiles[k].face_count = cnt;
     L.tiles[k].cut_start = cnt - cut;
     max_faces = std::max(max_faces, cnt);
@@ -645,59 +742,15 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   L.face_lr.assign(NF, 0);
   L.slot_nbr.assign((size_t)6 * L.slot_stride, 0xFFFF);
   L.tile_halo.assign((size_t)n_tiles * L.halo_stride, -1);
-  const char *fo_env = getenv("MINIAERO_FACE_ORDER");
-  const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
-  const bool pack = !by_cell && !(fo_env && !strcmp(fo_env, "slot"));
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
     const size_t fcp = (size_t)round_up(T.face_count, 16);
     const int shift = T.cell_start & 1, halo_base = round_up(shift + T.cell_count, 2);
-    // closed / boundary faces first, cut faces last.  Inside each group the faces are listed by slot (direction),
-    // then by cell — consecutive faces read consecutive own cells and consecutive neighbours — and, for the staged
-    // FAST kernels, that list is re-packed half-warp by half-warp so that the 16 lanes of a shared-memory wavefront
-    // read 16 different banks (pack_conflict_free; MINIAERO_FACE_ORDER=slot keeps the plain list).
-    // MINIAERO_FACE_ORDER=cell (and STRICT) keeps (cell, slot) order (the gather kernels' L1 locality).
-    struct Emit {
-      int c, s;
-    };
-    std::vector<Emit> group[2];  // 0 closed / boundary, 1 cut
-    std::vector<PackItem> pitems[2];
-    for (int it = 0; it < 6 * T.cell_count; ++it) {
-      const int c = T.cell_start + (by_cell ? it / 6 : it % T.cell_count);
-      const int s = by_cell ? it % 6 : it / T.cell_count;
-      if (!emits(T, c, s)) continue;
-      const bool cut = is_cut(T, c, s);
-      group[cut].push_back({c, s});
-      if (pack) {
-        const SlotInfo si = mesh.info(L.new2old[c], s);
-        const int side = si.side, own = shift + (c - T.cell_start);
-        const int oth = si.other;
-        PackItem pi;
-        if (cut) {
-          pi = {own, -1, side == 0 ? 2 : 3, 0};
-        } else if (oth < 0) {
-          pi = {own, -1, 2, 0};
-        } else {
-          const int op = shift + (L.old2new[oth] - T.cell_start);
-          pi = side == 0 ? PackItem{own, op, 0, 1} : PackItem{op, own, 0, 1};
-        }
-        pitems[cut].push_back(pi);
-      }
-    }
-    std::vector<int> porder[2];
-    for (int g = 0; g < 2; ++g) {
-      if (pack) {
-        // the closed group follows the cut group in the kernel's work-item numbering
-        pack_conflict_free(pitems[g], g == 0 ? (int)(group[1].size() & 15) : 0, porder[g]);
-      } else {
-        porder[g].resize(group[g].size());
-        for (size_t i = 0; i < group[g].size(); ++i) porder[g][i] = (int)i;
-      }
-    }
+    const std::shared_ptr<const TileOrder> O = order_of(T);
     for (int g = 0; g < 2; ++g)
-    for (size_t q = 0; q < group[g].size(); ++q) {
-      const int c = group[g][porder[g][q]].c, s = group[g][porder[g][q]].s;
+    for (size_t q = 0; q < O->lc[g].size(); ++q) {
+      const int c = T.cell_start + O->lc[g][q], s = O->slot[g][q];
       const int oldc = L.new2old[c];
       {
         const bool cut = g == 1;
