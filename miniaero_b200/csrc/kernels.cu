@@ -576,7 +576,7 @@ using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
 #ifndef MA_C128_GB1
 #define MA_C128_GB1 4
 #endif
-using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 8x4x4 / 4x4x8 bricks (flux: 12 warps per SM, 168 registers, no spills)
+using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 4x4x8 / 8x4x4 bricks (flux: 16 warps per SM at 124 registers, no spills)
 #ifndef MA_C256_FB
 #define MA_C256_FB 1
 #endif
@@ -786,11 +786,12 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, PERSIST ? CAP::GRAD_MINB : 
 
 // ---- sweep 2: face fluxes + slot-ordered gather + RK stage update -----------------------------------
 // Shared memory: sRec[NREC][RC] cell records (V 5, gradient 15, limiter 5, centroid 3) of the tile's own cells;
-// sG[6][FC] face geometry, overwritten face by face with the flux; sRK[11][RC] volume, Un, Acc of the own
-// cells; sLR[FC] tile-local face connectivity; sSlot[6][SC] slot map.  All of it arrives by bulk copies.
+// sG[6][FC] face geometry, overwritten face by face with the flux; sLR[FC] tile-local face connectivity;
+// sSlot[6][SC] slot map; optionally (MA_FLUX_RK_STAGED) sRK[11][RC] volume, Un, Acc of the own cells — by default
+// those are read from global memory in phase 2.  All of it arrives by bulk copies.
 // The record of the outside cell of a cut face never touches shared memory: the thread that will evaluate that
 // face gathers it straight into registers before it waits for the copies, so the gather's latency hides behind
-// the copies and the per-CTA footprint stays small enough for three resident CTAs per SM.
+// the copies and the per-CTA footprint (54 KB) stays small enough for four resident CTAs per SM.
 //   phase 1  thread per tile face (cut faces first): limited extrapolation of both cell records to the face
 //            (Flux.h:109-132), Roe flux (+ viscous flux), or the boundary-condition flux
 //   phase 2  thread per own cell: gather of the six face fluxes in slot order (Flux.h:216-227), RK update
