@@ -31,6 +31,8 @@ VARIANTS = {
     "c256b2": ["-DMA_C256_FB=2"],
     "t128b3p": ["-DMA_FLUX_PREFETCH_AHEAD=444"] + OLD,
     "g5": ["-DMA_C128_GB1=5"],
+    "xg_copyonly": ["-DMA_GRAD_EXPERIMENT=1"],
+    "xg_computeonly": ["-DMA_GRAD_EXPERIMENT=2"],
     "x_copyonly": ["-DMA_FLUX_EXPERIMENT=1"],
     "x_computeonly": ["-DMA_FLUX_EXPERIMENT=2"],
     "x_merged": ["-DMA_FLUX_EXPERIMENT=3"] + OLD,
