@@ -589,8 +589,9 @@ using Cap256 = TileCap<256, 896, 256, 256, 1, 2, 256, MA_C256_FB>;  // 8x8x4 / 4
 
 // ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
 // One own cell: neighbours (sV), face normals and centroids (sG) from shared memory; sn[s] = slot_face | slot_nbr << 16
-template <bool SECOND, int FC, int LS>
-MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const double *__restrict__ sV, int pos,
+// GLOBAL_G: the geometry is read from the tile's run in global memory (component stride gstride) instead of the staged copy
+template <bool SECOND, int LS, bool GLOBAL_G>
+MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const int gstride, const double *__restrict__ sV, int pos,
                               const unsigned (&sn)[6], double vol, const double (&xc)[3], int c, int stride,
                               double *__restrict__ grad, double *__restrict__ lim) {
   double V[5], g[5][3], mn[5], mx[5];
@@ -607,7 +608,7 @@ MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const double *__res
     const unsigned nb = sn[s] >> 16;
     double an[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) an[d] = flip_sign_if(sG[d * FC + e], right);
+    for (int d = 0; d < 3; ++d) an[d] = flip_sign_if(GLOBAL_G ? __ldg(sG + d * gstride + e) : sG[d * gstride + e], right);
     if (nb != 0xFFFFu) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
@@ -654,7 +655,7 @@ MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const double *__res
       double dist = 0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        disp[d] = sG[(3 + d) * FC + e] - xc[d];  // StencilLimiter.h:425-433
+        disp[d] = (GLOBAL_G ? __ldg(sG + (3 + d) * gstride + e) : sG[(3 + d) * gstride + e]) - xc[d];  // StencilLimiter.h:425-433
         dist = fma(disp[d], disp[d], dist);
       }
 #pragma unroll
@@ -678,12 +679,16 @@ MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const double *__res
 // out of one shared-memory stage, the bulk copies and the outside-cell gathers of tile i+1 land in the other
 // stage, and the tile descriptor / outside-cell ids of tile i+2 are on their way to registers: no load on the
 // arithmetic's critical path after the first tile.  Thread per own cell (blockDim >= cells of a tile).
-template <bool SECOND, class CAP, bool PERSIST>
-__global__ void __launch_bounds__(CAP::GRAD_THREADS, PERSIST ? CAP::GRAD_MINB : CAP::GRAD_MINB1)
+// GDIRECT (persistent only; MINIAERO_GRAD_PERSIST=2): the face geometry is not staged — a stage is the 12 KB of cell
+// states, so two stages fit under four resident CTAs — but read from the tile's run in global memory by the cell
+// threads, after a bulk L2 prefetch issued one tile ahead.
+template <bool SECOND, class CAP, bool PERSIST, bool GDIRECT = false>
+__global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP::GRAD_MINB : CAP::GRAD_MINB1)
     grad_limiter_tma_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
                             double *__restrict__ lim, int tile_begin, int ntiles) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NG = SECOND ? 6 : 3;  // normal (+ centroid)
+  constexpr int NG = GDIRECT ? 0 : (SECOND ? 6 : 3);  // staged geometry components: normal (+ centroid)
+  constexpr int NGC = SECOND ? 6 : 3;                 // geometry components the arithmetic reads
   constexpr int FC = CAP::FC, LS = CAP::LS;
   constexpr int STAGE = NG * FC + 5 * LS;  // doubles per stage: sG[NG][FC], sV[5][LS]
   constexpr int HPT = (CAP::HC + CAP::GRAD_THREADS - 1) / CAP::GRAD_THREADS;  // outside cells per thread
@@ -727,6 +732,8 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, PERSIST ? CAP::GRAD_MINB : 
       __syncwarp();
       // generic-proxy reads of this stage (ordered before by the CTA barrier) precede the copy engine's writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (GDIRECT && tid == 31)  // the geometry run of this tile: into L2 now, read by the cell threads one tile later
+        bulk_prefetch_l2(m.face_geom + (size_t)6 * T.face_start, (unsigned)NGC * gbytes);
       if (MA_GRAD_EXPERIMENT == 2) {
         if (tid == 0) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(NG * gbytes + 5 * vbytes) : "memory");
       } else if (tid < NG)
@@ -791,8 +798,13 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, PERSIST ? CAP::GRAD_MINB : 
       }
     } else if (tid < T0.cell_count) {
       const double *sG = sbase + st * STAGE, *sV = sG + NG * FC;
-      grad_limiter_cell<SECOND, FC, LS>(sG, sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc, T0.cell_start + tid,
-                                        m.stride, grad, lim);
+      if (GDIRECT)
+        grad_limiter_cell<SECOND, LS, true>(m.face_geom + (size_t)6 * T0.face_start, (int)((unsigned)(T0.face_count + 15) & ~15u),
+                                            sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc, T0.cell_start + tid,
+                                            m.stride, grad, lim);
+      else
+        grad_limiter_cell<SECOND, LS, false>(sG, FC, sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc,
+                                             T0.cell_start + tid, m.stride, grad, lim);
     }
     if (!has1) break;
     __syncthreads();  // every read of stage st is done before tile i+2 is copied into it
@@ -1349,13 +1361,15 @@ int tile_class_threads(int cls, int which) {
 // MINIAERO_GRAD_PERSIST=1: the gradient kernel as a persistent, double-buffered pipeline (tile i+1 is copied while
 // tile i is computed).  Measured slower than one tile per CTA (0.77 vs 0.73 ms at 8.4 M cells): the kernel is bound
 // by FP64 issue and warp count, not by the copy latency, and the second stage costs one resident CTA per SM.
-static bool grad_persistent() {
+static int grad_persistent() {  // 0: one tile per CTA, 1: persistent, 2: persistent with the geometry read directly
   const char *e = getenv("MINIAERO_GRAD_PERSIST");
-  return e && e[0] == '1';
+  return e && (e[0] == '1' || e[0] == '2') ? e[0] - '0' : 0;
 }
 template <class CAP>
 static size_t grad_tma_smem(bool second) {  // one or two stages + two mbarriers
-  return (size_t)(grad_persistent() ? 2 : 1) * ((second ? 6 : 3) * CAP::FC + 5 * CAP::LS) * 8 + 16;
+  const int mode = grad_persistent();
+  const int ng = mode == 2 ? 0 : (second ? 6 : 3);
+  return (size_t)(mode ? 2 : 1) * (ng * CAP::FC + 5 * CAP::LS) * 8 + 16;
 }
 // grid of a persistent kernel: resident CTAs per SM x SMs of the current device
 static int persistent_ctas(int ctas_per_sm) {
@@ -1394,7 +1408,13 @@ template <class CAP>
 static cudaError_t launch_grad_tma(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                    int tile_begin, int ntiles, cudaStream_t st) {
   const size_t smem = grad_tma_smem<CAP>(second);
-  if (grad_persistent()) {
+  if (grad_persistent() == 2) {
+    const int grid = std::min(ntiles, persistent_ctas(CAP::GRAD_MINB1));
+    if (second)
+      grad_limiter_tma_kernel<true, CAP, true, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+    else
+      grad_limiter_tma_kernel<false, CAP, true, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+  } else if (grad_persistent()) {
     const int grid = std::min(ntiles, persistent_ctas(CAP::GRAD_MINB));
     if (second)
       grad_limiter_tma_kernel<true, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
@@ -1430,10 +1450,18 @@ static cudaError_t prepare_tma() {
   if (e != cudaSuccess) return e;                                                          \
   e = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
   if (e != cudaSuccess) return e;
+  MA_SET((grad_limiter_tma_kernel<true, CAP, true, true>), grad_tma_smem<CAP>(true))
+  MA_SET((grad_limiter_tma_kernel<false, CAP, true, true>), grad_tma_smem<CAP>(false))
   MA_SET((grad_limiter_tma_kernel<true, CAP, true>), grad_tma_smem<CAP>(true))
   MA_SET((grad_limiter_tma_kernel<false, CAP, true>), grad_tma_smem<CAP>(false))
   MA_SET((grad_limiter_tma_kernel<true, CAP, false>), grad_tma_smem<CAP>(true))
   MA_SET((grad_limiter_tma_kernel<false, CAP, false>), grad_tma_smem<CAP>(false))
+  // the direct-geometry gradient variant stages 23 KB per CTA: leave the rest of the SM's array to L1, where the
+  // second reader of a face's geometry finds it
+  e = cudaFuncSetAttribute((grad_limiter_tma_kernel<true, CAP, true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 45);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute((grad_limiter_tma_kernel<false, CAP, true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 45);
+  if (e != cudaSuccess) return e;
   MA_SET((flux_rk_tma_kernel<true, true, CAP>), (flux_tma_smem<true, true, CAP>()))
   MA_SET((flux_rk_tma_kernel<true, false, CAP>), (flux_tma_smem<true, false, CAP>()))
   MA_SET((flux_rk_tma_kernel<false, true, CAP>), (flux_tma_smem<false, true, CAP>()))
