@@ -385,25 +385,32 @@ def gpu_arm(args):
     # pinned input state, its own pinned output), so the upload of batch i+1 and the download of batch i-1 run on
     # their own streams while batch i is stepped.  Two input states (the solution at two different times) alternate.
     pipe_steps = max(args.steps, e2e_steps)
-    for _ in range(2):   # warm-up (allocates the device staging buffers)
-        solver.submit(hin.data_ptr(), hout.data_ptr(), 1)
-    solver.synchronize()
-    hin2 = hout.clone().pin_memory()
-    houts = [hout, torch.empty_like(hout).pin_memory()]
-    barrier()
-    w0 = time.perf_counter()
-    for i in range(pipe_steps):
-        solver.submit((hin, hin2)[i & 1].data_ptr(), houts[i & 1].data_ptr(), 1)
-    solver.synchronize()
-    pipe_s = max_over_ranks(time.perf_counter() - w0)
-    finite_pipe = bool(torch.isfinite(houts[0]).all().item() and torch.isfinite(houts[1]).all().item())
-    e2e = {"value": total_cells * pipe_steps / pipe_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
-           "d2h_bytes_per_step": nbytes, "steps": pipe_steps, "ms_per_step": 1e3 * pipe_s / pipe_steps,
-           "what": "per step ma_solver_submit(pinned host in, pinned host out, 1): upload of the batch's state, one RK4 "
-                   "step, download of the new state; consecutive independent batches pipelined over three streams "
-                   "(fill and drain of the pipeline inside the timed region)",
-           "result_finite": finite_pipe, "serial_chain": serial}
-    del hin2, houts
+    try:
+        for _ in range(2):   # warm-up (allocates the device staging buffers: four more copies of the state)
+            solver.submit(hin.data_ptr(), hout.data_ptr(), 1)
+        solver.synchronize()
+        hin2 = hout.clone().pin_memory()
+        houts = [hout, torch.empty_like(hout).pin_memory()]
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(pipe_steps):
+            solver.submit((hin, hin2)[i & 1].data_ptr(), houts[i & 1].data_ptr(), 1)
+        solver.synchronize()
+        pipe_s = max_over_ranks(time.perf_counter() - w0)
+        finite_pipe = bool(torch.isfinite(houts[0]).all().item() and torch.isfinite(houts[1]).all().item())
+        e2e = {"value": total_cells * pipe_steps / pipe_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": pipe_steps, "ms_per_step": 1e3 * pipe_s / pipe_steps,
+               "what": "per step ma_solver_submit(pinned host in, pinned host out, 1): upload of the batch's state, one "
+                       "RK4 step, download of the new state; consecutive independent batches pipelined over three "
+                       "streams (fill and drain of the pipeline inside the timed region)",
+               "result_finite": finite_pipe, "serial_chain": serial}
+        del hin2, houts
+    except (ma.MiniAeroError, RuntimeError) as ex:
+        # no room for the pipeline's staging buffers next to a solver that fills the device (every rank sizes alike):
+        # the dependent chain is the end-to-end number then
+        e2e = {"value": serial["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": nbytes, "steps": serial["steps"], "ms_per_step": serial["ms_per_step"],
+               "what": serial["what"], "pipelined_unavailable": str(ex)[:200]}
     # the reference's own call shape (Main.C:139-141): one Solve() of K steps, state up once, result down once
     barrier()
     w0 = time.perf_counter()
