@@ -484,17 +484,11 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     uint32_t local;
     int cell;
   };
-  std::vector<Key> keys((size_t)n_owned);
-#pragma omp parallel for schedule(static)
-  for (long c = 0; c < n_owned; ++c) {
-    long q[3], t[3], l[3];
-    mesh.bin(c, q);
-    for (int d = 0; d < 3; ++d) {
-      t[d] = q[d] / L.tile_dims[d];
-      l[d] = q[d] % L.tile_dims[d];
-    }
-    keys[c].tile = linear_order ? ((uint64_t)t[0] * ntile_d[1] + t[1]) * ntile_d[2] + t[2] : morton3(t[0], t[1], t[2]);
-    uint32_t local = (uint32_t)((l[0] * L.tile_dims[1] + l[1]) * L.tile_dims[2] + l[2]);
+  auto tile_key_of = [&](long t0, long t1, long t2) -> uint64_t {
+    return linear_order ? ((uint64_t)t0 * ntile_d[1] + t1) * ntile_d[2] + t2 : morton3(t0, t1, t2);
+  };
+  auto local_key_of = [&](long l0, long l1, long l2) -> uint32_t {
+    uint32_t local = (uint32_t)((l0 * L.tile_dims[1] + l1) * L.tile_dims[2] + l2);
     if (swizzle) {
       // 4 x 4 x 8 bricks, z fastest: the cells of a brick SURFACE (the own cells of the cut faces) would share few
       // shared-memory banks (z surface: 2 of the 16 double-word residues, y surface: 8).  XOR-ing the low four bits
@@ -503,19 +497,70 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
       const uint32_t h = local >> 4;
       local ^= ((h >> 1) & 3u) | ((h & 1u) << 2) | (((h >> 2) & 1u) << 3);
     }
-    keys[c].local = local;
-    keys[c].cell = (int)c;
-  }
+    return local;
+  };
   auto key_less = [](const Key &a, const Key &b) {
     if (a.tile != b.tile) return a.tile < b.tile;
     if (a.local != b.local) return a.local < b.local;
     return a.cell < b.cell;
   };
+  std::vector<Key> keys((size_t)n_owned);
+  if (Mesh::kStructured && (long)nbin[0] * nbin[1] * nbin[2] == (long)n_owned) {
+    // a structured block: the sorted key array is written tile by tile (tiles sorted by key, the cells of a brick by
+    // their local key), with no sort over the cells; cell (i, j, k) has id (i * ny + j) * nz + k
+    struct TileRef {
+      uint64_t key;
+      int t[3];
+      long first;
+    };
+    std::vector<TileRef> refs;
+    refs.reserve((size_t)(ntile_d[0] * ntile_d[1] * ntile_d[2]));
+    for (long a = 0; a < ntile_d[0]; ++a)
+      for (long b = 0; b < ntile_d[1]; ++b)
+        for (long c = 0; c < ntile_d[2]; ++c) refs.push_back({tile_key_of(a, b, c), {(int)a, (int)b, (int)c}, 0});
+    std::sort(refs.begin(), refs.end(), [](const TileRef &x, const TileRef &y) { return x.key < y.key; });
+    long next = 0;
+    for (TileRef &r : refs) {
+      r.first = next;
+      long cnt = 1;
+      for (int d = 0; d < 3; ++d) cnt *= std::min<long>(L.tile_dims[d], nbin[d] - (long)r.t[d] * L.tile_dims[d]);
+      next += cnt;
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long ti = 0; ti < (long)refs.size(); ++ti) {
+      const TileRef &r = refs[ti];
+      long o[3], e[3];
+      for (int d = 0; d < 3; ++d) {
+        o[d] = (long)r.t[d] * L.tile_dims[d];
+        e[d] = std::min<long>(L.tile_dims[d], nbin[d] - o[d]);
+      }
+      Key *out = keys.data() + r.first;
+      long w = 0;
+      for (long a = 0; a < e[0]; ++a)
+        for (long b = 0; b < e[1]; ++b)
+          for (long c = 0; c < e[2]; ++c)
+            out[w++] = {r.key, local_key_of(a, b, c), (int)(((o[0] + a) * nbin[1] + (o[1] + b)) * nbin[2] + (o[2] + c))};
+      std::sort(out, out + w, key_less);
+    }
+  } else {
+#pragma omp parallel for schedule(static)
+    for (long c = 0; c < n_owned; ++c) {
+      long q[3], t[3], l[3];
+      mesh.bin(c, q);
+      for (int d = 0; d < 3; ++d) {
+        t[d] = q[d] / L.tile_dims[d];
+        l[d] = q[d] % L.tile_dims[d];
+      }
+      keys[c].tile = tile_key_of(t[0], t[1], t[2]);
+      keys[c].local = local_key_of(l[0], l[1], l[2]);
+      keys[c].cell = (int)c;
+    }
 #ifdef _OPENMP
-  __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
+    __gnu_parallel::sort(keys.begin(), keys.end(), key_less);
 #else
-  std::sort(keys.begin(), keys.end(), key_less);
+    std::sort(keys.begin(), keys.end(), key_less);
 #endif
+  }
 
   lap("bin + sort cells");
   // ---- 3. cut tiles, classify (touches a ghost?), order interior tiles first, renumber
