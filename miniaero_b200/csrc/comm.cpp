@@ -8,7 +8,10 @@
 
 #include <dlfcn.h>
 
+#include <functional>
+
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "host_common.h"
@@ -40,11 +43,7 @@ struct NcclApi {
   std::string error;
 };
 
-NcclApi &api() {
-  static NcclApi a;
-  static bool tried = false;
-  if (tried) return a;
-  tried = true;
+void load_api(NcclApi &a) {
   const char *env = getenv("MINIAERO_NCCL_LIB");
   const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
   for (const char *n : names) {
@@ -53,8 +52,9 @@ NcclApi &api() {
     if (a.handle) break;
   }
   if (!a.handle) {
-    a.error = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
-    return a;
+    const char *e = dlerror();  // one call: dlerror() clears the message it returns
+    a.error = std::string("cannot dlopen libnccl.so.2: ") + (e ? e : "?");
+    return;
   }
 #define MA_SYM(field, name)                                      \
   a.field = (decltype(a.field))dlsym(a.handle, name);            \
@@ -68,6 +68,12 @@ NcclApi &api() {
   MA_SYM(Recv, "ncclRecv")
   MA_SYM(GetErrorString, "ncclGetErrorString")
 #undef MA_SYM
+}
+
+NcclApi &api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, load_api, std::ref(a));
   return a;
 }
 
@@ -94,6 +100,7 @@ int comm_exchange(ma_comm *c, const double *sendbuf, double *recvbuf, int row, i
                   const int *send_count, const int *recv_count, cudaStream_t st) {
   if (!c) return ma_set_error(MA_ERR_NCCL, "halo exchange requested without a communicator");
   NcclApi &a = api();
+  if (!a.error.empty()) return ma_set_error(MA_ERR_NCCL, a.error);
   int rc = a.GroupStart();
   if (rc) return nccl_fail("ncclGroupStart", rc);
   size_t so = 0, ro = 0;
@@ -101,11 +108,17 @@ int comm_exchange(ma_comm *c, const double *sendbuf, double *recvbuf, int row, i
     const size_t ns = (size_t)send_count[p] * row, nr = (size_t)recv_count[p] * row;
     if (ns) {
       rc = a.Send(sendbuf + so, ns, kNcclDouble, peer_rank[p], c->comm, st);
-      if (rc) return nccl_fail("ncclSend", rc);
+      if (rc) {
+        a.GroupEnd();  // never leave the thread in group mode
+        return nccl_fail("ncclSend", rc);
+      }
     }
     if (nr) {
       rc = a.Recv(recvbuf + ro, nr, kNcclDouble, peer_rank[p], c->comm, st);
-      if (rc) return nccl_fail("ncclRecv", rc);
+      if (rc) {
+        a.GroupEnd();
+        return nccl_fail("ncclRecv", rc);
+      }
     }
     so += ns;
     ro += nr;

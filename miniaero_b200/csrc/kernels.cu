@@ -551,16 +551,6 @@ MA_DEV void cp_async8s(unsigned dst, const double *gmem_src) {
 #ifndef MA_FLUX_PREFETCH_AHEAD
 #define MA_FLUX_PREFETCH_AHEAD 0
 #endif
-// timing experiments only (wrong results): 1 = copies and gathers but no face arithmetic, 2 = face arithmetic on
-// whatever shared memory holds (only the connectivity is copied)
-#ifndef MA_FLUX_EXPERIMENT
-#define MA_FLUX_EXPERIMENT 0
-#endif
-// the same for the staged gradient kernel: 1 = copies and gathers, zeros stored instead of the arithmetic's results;
-// 2 = arithmetic on whatever shared memory holds (no copies, no gathers)
-#ifndef MA_GRAD_EXPERIMENT
-#define MA_GRAD_EXPERIMENT 0
-#endif
 // Capacity class of a tile: the staged kernels are compiled for a few (cells, faces, cut faces) capacities so
 // that every shared-memory stride is a compile-time constant.
 template <int CELLS, int FACES, int HALO, int GRAD_T, int GRAD_B, int GRAD_B1, int FLUX_T, int FLUX_B>
@@ -734,16 +724,14 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (GDIRECT && tid == 31)  // the geometry run of this tile: into L2 now, read by the cell threads one tile later
         bulk_prefetch_l2(m.face_geom + (size_t)6 * T.face_start, (unsigned)NGC * gbytes);
-      if (MA_GRAD_EXPERIMENT == 2) {
-        if (tid == 0) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(NG * gbytes + 5 * vbytes) : "memory");
-      } else if (tid < NG)
+      if (tid < NG)
         bulk_g2s(smem_addr(sG + tid * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)tid * fcp, gbytes, bar);
       else if (tid < NG + 5)
         bulk_g2s(smem_addr(sV + (tid - NG) * LS), V_ + (size_t)(tid - NG) * m.stride + (T.cell_start - shift), vbytes, bar);
     }
 #pragma unroll
     for (int j = 0; j < HPT; ++j) {
-      if (MA_GRAD_EXPERIMENT != 2 && ids[j] >= 0) {
+      if (ids[j] >= 0) {
         const int h = tid + j * CAP::GRAD_THREADS;
 #pragma unroll
         for (int k = 0; k < 5; ++k) cp_async8s(smem_addr(sV + k * LS + hb + h), V_ + (size_t)k * m.stride + ids[j]);
@@ -785,18 +773,7 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
       if (t + 3 * G < ntiles) T3 = tiles[t + 3 * G];       // consumed two iterations from now
     }
     mbar_wait(bar0 + 8 * st, (unsigned)(i >> 1) & 1u);
-    if (MA_GRAD_EXPERIMENT == 1) {
-      if (tid < T0.cell_count) {
-        const int c = T0.cell_start + tid;
-        const double z = (sbase[st * STAGE + tid] == 1.2345e300) ? 1.0 : 0.0;  // keeps the staged data alive
-#pragma unroll
-        for (int k = 0; k < 15; ++k) grad[(size_t)k * m.stride + c] = z;
-        if (SECOND) {
-#pragma unroll
-          for (int k = 0; k < 5; ++k) lim[(size_t)k * m.stride + c] = z;
-        }
-      }
-    } else if (tid < T0.cell_count) {
+    if (tid < T0.cell_count) {
       const double *sG = sbase + st * STAGE, *sV = sG + NG * FC;
       if (GDIRECT)
         grad_limiter_cell<SECOND, LS, true>(m.face_geom + (size_t)6 * T0.face_start, (int)((unsigned)(T0.face_count + 15) & ~15u),
@@ -859,56 +836,58 @@ struct RegRecord {
   MA_DEV double x(int d) const { return r[R::R_X + d]; }
 };
 // one side of an interior face: primitives limited-extrapolated to the face centroid (Flux.h:109-132) and this
-// cell's share of the gradient sum (Flux.h:146-149; rows 1..4, the density gradient is never used)
+// cell's share of the viscous traction.  Viscous_Flux.h:65-98 is linear in the face gradient 0.5 (g_l + g_r)
+// (Flux.h:146-149), so each side contributes q = tau(g) . a (momentum rows) and hh = grad T . a on its own: four
+// running sums instead of the twelve gradient sums (the density gradient is never used).
 template <bool SECOND, bool VISCOUS, bool FIRST, class REC>
-MA_DEV void face_side(const REC &rec, const double (&xf)[3], double (&V)[5], double (&gs)[5][3]) {
+MA_DEV void face_side(const REC &rec, const double (&xf)[3], const double (&n)[3], double (&V)[5], double (&q)[4]) {
+  double dx[3];
   if (SECOND) {
-    double dx[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) dx[d] = xf[d] - rec.x(d);
+  }
+  double gv[5][3];
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      double g[3];
+  for (int k = 0; k < 5; ++k) {
+    if (SECOND || (VISCOUS && k > 0)) {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        g[d] = rec.g(k, d);
-        if (VISCOUS && k > 0) gs[k][d] = FIRST ? g[d] : gs[k][d] + g[d];
-      }
-      const double t = fma(dx[2], g[2], fma(dx[1], g[1], dx[0] * g[0]));  // Flux.h:114-121
-      V[k] = fma(t, rec.lim(k), rec.v(k));                               // Flux.h:124-127
+      for (int d = 0; d < 3; ++d) gv[k][d] = rec.g(k, d);
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) V[k] = rec.v(k);
-    if (VISCOUS) {
-#pragma unroll
-      for (int k = 1; k < 5; ++k)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) gs[k][d] = FIRST ? rec.g(k, d) : gs[k][d] + rec.g(k, d);
+    if (SECOND) {
+      const double t = fma(dx[2], gv[k][2], fma(dx[1], gv[k][1], dx[0] * gv[k][0]));  // Flux.h:114-121
+      V[k] = fma(t, rec.lim(k), rec.v(k));                                         // Flux.h:124-127
+    } else {
+      V[k] = rec.v(k);
     }
+  }
+  if (VISCOUS) {
+    const double third_div = (gv[1][0] + gv[2][1] + gv[3][2]) * (1.0 / 3.0);
+    const double txx = gv[1][0] - third_div, tyy = gv[2][1] - third_div, tzz = gv[3][2] - third_div;
+    const double txy = 0.5 * (gv[1][1] + gv[2][0]), txz = 0.5 * (gv[1][2] + gv[3][0]);
+    const double tyz = 0.5 * (gv[2][2] + gv[3][1]);
+    const double q0 = txx * n[0] + txy * n[1] + txz * n[2];
+    const double q1 = txy * n[0] + tyy * n[1] + tyz * n[2];
+    const double q2 = txz * n[0] + tyz * n[1] + tzz * n[2];
+    const double hh = gv[4][0] * n[0] + gv[4][1] * n[1] + gv[4][2] * n[2];
+    q[0] = FIRST ? q0 : q[0] + q0;
+    q[1] = FIRST ? q1 : q[1] + q1;
+    q[2] = FIRST ? q2 : q[2] + q2;
+    q[3] = FIRST ? hh : q[3] + hh;
   }
 }
 // Roe flux (Roe_Flux.h:49-265) minus the Newtonian viscous flux (Viscous_Flux.h:65-98) at the face state
-// 0.5 (Vl + Vr) (Flux.h:142-143) with gs = 2 x face gradient
+// 0.5 (Vl + Vr) (Flux.h:142-143); q = (tau . a, grad T . a) of TWICE the face gradient (both sides' shares summed)
 template <bool VISCOUS>
-MA_DEV void interior_flux(const double (&Vl)[5], const double (&Vr)[5], const double (&gs)[5][3], const FaceGeom &G,
+MA_DEV void interior_flux(const double (&Vl)[5], const double (&Vr)[5], const double (&q)[4], const FaceGeom &G,
                           double (&flux)[5]) {
   face_roe_flux(Vl, Vr, G, flux);
   if (VISCOUS) {
-    const double third_div = (gs[1][0] + gs[2][1] + gs[3][2]) * (1.0 / 3.0);
-    const double txx = gs[1][0] - third_div, tyy = gs[2][1] - third_div, tzz = gs[3][2] - third_div;
-    const double txy = 0.5 * (gs[1][1] + gs[2][0]), txz = 0.5 * (gs[1][2] + gs[3][0]);
-    const double tyz = 0.5 * (gs[2][2] + gs[3][1]);
-    const double q0 = txx * G.n[0] + txy * G.n[1] + txz * G.n[2];
-    const double q1 = txy * G.n[0] + tyy * G.n[1] + tyz * G.n[2];
-    const double q2 = txz * G.n[0] + tyz * G.n[1] + tzz * G.n[2];
-    const double hh = gs[4][0] * G.n[0] + gs[4][1] * G.n[1] + gs[4][2] * G.n[2];
     const double mu = compute_viscosity(0.5 * (Vl[4] + Vr[4]));
-    const double uq = (Vl[1] + Vr[1]) * q0 + (Vl[2] + Vr[2]) * q1 + (Vl[3] + Vr[3]) * q2;
-    flux[1] -= mu * q0;
-    flux[2] -= mu * q1;
-    flux[3] -= mu * q2;
-    flux[4] -= fma(0.5 * mu, uq, 0.5 * compute_thermal_conductivity(mu) * hh);
+    const double uq = (Vl[1] + Vr[1]) * q[0] + (Vl[2] + Vr[2]) * q[1] + (Vl[3] + Vr[3]) * q[2];
+    flux[1] -= mu * q[0];
+    flux[2] -= mu * q[1];
+    flux[3] -= mu * q[2];
+    flux[4] -= fma(0.5 * mu, uq, 0.5 * compute_thermal_conductivity(mu) * q[3]);
   }
 }
 
@@ -994,22 +973,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     const int nrk = 1 + (a.kind != 2 ? 5 : 0) + (a.kind != 0 ? 5 : 0);
     if (tid == 0) mbar_arrive_expect_tx(bar, (NREC + (RKS ? nrk : 0)) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes);
     __syncwarp();
-    if (MA_FLUX_EXPERIMENT == 3) {  // the same bytes as four large requests (timing experiment)
-      if (tid == 0) asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(4u * 16384u) : "memory");
-      __syncwarp();
-      if (tid < 4)
-        bulk_g2s(smem_addr(sRec) + tid * 16384u, a.grad + (size_t)((blockIdx.x & 8191u) * 4u + tid) * 2048u, 16384u, bar);
-      if (tid < 32) {
-        const unsigned total = (NREC + (RKS ? nrk : 0)) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes;
-        if (tid == 0) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(total) : "memory");
-      }
-    } else
     for_each_run(T, [&](unsigned dst, const void *src, unsigned bytes, bool staged) {
-      if (MA_FLUX_EXPERIMENT == 2 && (const void *)src != (const void *)(m.face_lr + T.face_start) &&
-          !((const char *)src >= (const char *)m.slot_face && (const char *)src < (const char *)(m.slot_face + 6 * (size_t)m.slot_stride))) {
-        if (staged) asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        return;
-      }
       if (staged)
         bulk_g2s(dst, src, bytes, bar);
       else  // phase 2 reads this run from global memory: have it in L2 by then
@@ -1051,11 +1015,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     }
     mbar_cp_async_arrive(bar);
   }
-  if (MA_FLUX_EXPERIMENT == 2) {
-#pragma unroll
-    for (int k = 0; k < NREC; ++k) orec[k] = 1.0 + k;
-  } else if (my_outside >= 0)
-    gather_outside(my_outside);
+  if (my_outside >= 0) gather_outside(my_outside);
   if (XC == 0 && CUT2 > 0 && my_outside2 >= 0) {
     const int c = my_outside2;
 #pragma unroll
@@ -1097,27 +1057,20 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
       G.n[d] = sG[d * FC + e];
       xf[d] = SECOND ? sG[(3 + d) * FC + e] : 0.0;
     }
-    double Vl[5], Vr[5], gs[5][3], flux[5];
+    double Vl[5], Vr[5], gs[4], flux[5];
     // the outside record first: its registers are free before the own cell's record is read
     if (pr >= hb) {  // outside cell on the right
-      face_side<SECOND, VISCOUS, true>(outside, xf, Vr, gs);
-      face_side<SECOND, VISCOUS, false>(SRec{sRec + pl}, xf, Vl, gs);
+      face_side<SECOND, VISCOUS, true>(outside, xf, G.n, Vr, gs);
+      face_side<SECOND, VISCOUS, false>(SRec{sRec + pl}, xf, G.n, Vl, gs);
     } else {
-      face_side<SECOND, VISCOUS, true>(outside, xf, Vl, gs);
-      face_side<SECOND, VISCOUS, false>(SRec{sRec + pr}, xf, Vr, gs);
+      face_side<SECOND, VISCOUS, true>(outside, xf, G.n, Vl, gs);
+      face_side<SECOND, VISCOUS, false>(SRec{sRec + pr}, xf, G.n, Vr, gs);
     }
     interior_flux<VISCOUS>(Vl, Vr, gs, G, flux);
 #pragma unroll
     for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];  // this thread's own column: geometry is dead
   };
   int w = tid;
-  if (MA_FLUX_EXPERIMENT == 1 || MA_FLUX_EXPERIMENT == 3) {
-    double acc = 0;
-#pragma unroll
-    for (int k = 0; k < NREC; ++k) acc += orec[k];
-    if (acc == 1.2345e300) sG[tid] = acc;  // keeps the gather alive
-    w = nf;
-  }
   if (w < nh) {  // first cut face of this thread: outside record in registers
     cut_face(T.cut_start + w, RRec{orec});
     w += blockDim.x;
@@ -1144,9 +1097,9 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
       double xf[3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) xf[d] = SECOND ? sG[(3 + d) * FC + e] : 0.0;
-      double Vl[5], Vr[5], gs[5][3];
-      face_side<SECOND, VISCOUS, true>(SRec{sRec + pl}, xf, Vl, gs);
-      face_side<SECOND, VISCOUS, false>(SRec{sRec + (int)pr}, xf, Vr, gs);
+      double Vl[5], Vr[5], gs[4];
+      face_side<SECOND, VISCOUS, true>(SRec{sRec + pl}, xf, G.n, Vl, gs);
+      face_side<SECOND, VISCOUS, false>(SRec{sRec + (int)pr}, xf, G.n, Vr, gs);
       interior_flux<VISCOUS>(Vl, Vr, gs, G, flux);
     } else {
       // boundary face, always first order (Extrapolate_BC.h, Tangent_BC.h, Inflow_BC.h, NoSlip_BC.h)
@@ -1211,7 +1164,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       const unsigned sf = sSlot[s * SC + sshift + lc];
-      const int e = MA_FLUX_EXPERIMENT == 3 ? (int)(sf & 0xffu) : (int)(sf & 0x3fffu);
+      const int e = (int)(sf & 0x3fffu);
       const double sg = (sf & 0x8000u) ? dtv : -dtv;  // Flux.h:172-178: left slot holds -flux, right slot +flux
 #pragma unroll
       for (int k = 0; k < 5; ++k) Rs[k] = fma(sg, sG[k * FC + e], Rs[k]);

@@ -8,9 +8,14 @@
 //
 // Ranks: one process per GPU, rank / size taken from RANK / WORLD_SIZE (or OMPI_COMM_WORLD_* / PMI_*), device from
 // LOCAL_RANK.  The NCCL unique id travels through a file (MINIAERO_RENDEZVOUS, default
-// /tmp/miniaero_rdv.<MASTER_PORT or 0>): rank 0 writes it, the others poll — the only bootstrap the run needs,
-// standing in for MPI_Init (Main.C:61-63).
+// /tmp/miniaero_rdv.<MASTER_PORT or 0>.<launcher pid>[.<run id>]): rank 0 writes it, the others poll, rank 0 removes
+// it — the only bootstrap the run needs, standing in for MPI_Init (Main.C:61-63).
+#include <fcntl.h>
+#include <signal.h>
 #include <unistd.h>
+
+#include <cctype>
+#include <random>
 
 #include <chrono>
 #include <cstdio>
@@ -38,33 +43,89 @@ int env_int(std::initializer_list<const char *> names, int fallback) {
   exit(1);
 }
 
-// rank 0 publishes the NCCL id in a file, the other ranks wait for it
-bool exchange_id(int rank, unsigned char id[MA_COMM_ID_BYTES]) {
-  std::string path;
-  if (const char *p = getenv("MINIAERO_RENDEZVOUS")) {
-    path = p;
-  } else {
-    const char *port = getenv("MASTER_PORT");
-    path = std::string("/tmp/miniaero_rdv.") + (port ? port : "0");
+// Rank 0 publishes the NCCL id in a file, the other ranks wait for it.  Two things keep a launch from reading what an
+// earlier (possibly aborted) launch left behind under the same name:
+//  * the file name carries a per-launch token (MINIAERO_RENDEZVOUS overrides it): the launcher's run id when it exports
+//    one, and the parent process id — every rank of one torchrun / mpirun launch on a node is a child of the same agent;
+//  * a handshake: rank r > 0 first announces its process id in <file>.hello.<r>; rank 0 waits for an announcement from
+//    a LIVE process per rank, then publishes id + the process ids it saw; rank r accepts the file only if it names r's
+//    own process id.  A stale id file names dead processes and is ignored, a stale announcement is ignored by rank 0.
+// Files are created exclusively under a temporary name (O_EXCL | O_NOFOLLOW: no symlink games in /tmp) and renamed
+// into place; rank 0 removes the id file once its communicator exists (ncclCommInitRank returns only after every rank
+// has joined, i.e. has read the id), every other rank removes its announcement once it holds the id.
+std::string rendezvous_path() {
+  if (const char *p = getenv("MINIAERO_RENDEZVOUS")) return p;
+  const char *port = getenv("MASTER_PORT");
+  const char *run = getenv("TORCHELASTIC_RUN_ID");
+  std::string path = std::string("/tmp/miniaero_rdv.") + (port ? port : "0") + "." + std::to_string((long)getppid());
+  if (run && *run) {
+    path += ".";
+    for (const char *c = run; *c; ++c) path += (isalnum((unsigned char)*c) ? *c : '_');
   }
+  return path;
+}
+std::string g_rendezvous_file;  // rank 0: the file to remove (after the communicator exists, or at exit)
+void remove_rendezvous_file() {
+  if (!g_rendezvous_file.empty()) unlink(g_rendezvous_file.c_str());
+  g_rendezvous_file.clear();
+}
+bool write_file_atomically(const std::string &path, const void *buf, size_t n) {
+  const std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  unlink(tmp.c_str());
+  const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+  if (fd < 0) return false;
+  const bool ok = write(fd, buf, n) == (ssize_t)n;
+  close(fd);
+  if (!ok || rename(tmp.c_str(), path.c_str()) != 0) {
+    unlink(tmp.c_str());
+    return false;
+  }
+  return true;
+}
+bool read_file(const std::string &path, void *buf, size_t n) {
+  const int fd = open(path.c_str(), O_RDONLY | O_NOFOLLOW);
+  if (fd < 0) return false;
+  const ssize_t got = read(fd, buf, n);
+  close(fd);
+  return got == (ssize_t)n;
+}
+bool exchange_bytes(int rank, int nranks, unsigned char *buf, size_t n, const std::string &path) {
+  const int kTries = 6000;  // x 100 ms = 10 minutes: rank 0 may still be generating its mesh
+  std::vector<unsigned char> rec(n + sizeof(long long) * (size_t)nranks);
+  long long *pids = reinterpret_cast<long long *>(rec.data() + n);
   if (rank == 0) {
-    if (ma_comm_get_unique_id(id)) return false;
-    const std::string tmp = path + ".tmp";
-    FILE *f = fopen(tmp.c_str(), "wb");
-    if (!f) return false;
-    const bool ok = fwrite(id, 1, MA_COMM_ID_BYTES, f) == MA_COMM_ID_BYTES;
-    fclose(f);
-    return ok && rename(tmp.c_str(), path.c_str()) == 0;
-  }
-  for (int tries = 0; tries < 6000; ++tries) {  // up to 10 minutes: rank 0 may still be generating its mesh
-    if (FILE *f = fopen(path.c_str(), "rb")) {
-      const size_t n = fread(id, 1, MA_COMM_ID_BYTES, f);
-      fclose(f);
-      if (n == MA_COMM_ID_BYTES) return true;
+    pids[0] = (long long)getpid();
+    for (int r = 1; r < nranks; ++r) {
+      const std::string hello = path + ".hello." + std::to_string(r);
+      long long p = 0;
+      int tries = 0;
+      while (!(read_file(hello, &p, sizeof(p)) && p > 0 && kill((pid_t)p, 0) == 0)) {
+        if (++tries > kTries) return false;
+        std::this_thread::sleep_for(std::chrono::milliseconds(100));
+      }
+      pids[r] = p;
     }
-    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+    memcpy(rec.data(), buf, n);
+    if (!write_file_atomically(path, rec.data(), rec.size())) return false;
+    g_rendezvous_file = path;
+    atexit(remove_rendezvous_file);
+    return true;
   }
-  return false;
+  const std::string hello = path + ".hello." + std::to_string(rank);
+  const long long me = (long long)getpid();
+  if (!write_file_atomically(hello, &me, sizeof(me))) return false;
+  bool ok = false;
+  for (int tries = 0; tries < kTries && !ok; ++tries) {
+    ok = read_file(path, rec.data(), rec.size()) && pids[rank] == me;
+    if (!ok) std::this_thread::sleep_for(std::chrono::milliseconds(100));
+  }
+  unlink(hello.c_str());
+  if (ok) memcpy(buf, rec.data(), n);
+  return ok;
+}
+bool exchange_id(int rank, int nranks, unsigned char id[MA_COMM_ID_BYTES]) {
+  if (rank == 0 && ma_comm_get_unique_id(id)) return false;
+  return exchange_bytes(rank, nranks, id, MA_COMM_ID_BYTES, rendezvous_path());
 }
 
 }  // namespace
@@ -73,7 +134,7 @@ int main(int argc, char **argv) {
   const auto t_start = Clock::now();
   std::string input = "miniaero.inp", yaml_dir = ".";
   int arith = MA_ARITH_FAST, precision = 0, tile[3] = {0, 0, 0}, limiter = MA_LIMITER_VENKAT;
-  bool yaml = true;
+  bool yaml = true, rdv_selftest = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() -> const char * {
@@ -90,6 +151,7 @@ int main(int argc, char **argv) {
     else if (a == "--precision") precision = atoi(next());
     else if (a == "--yaml") yaml_dir = next();
     else if (a == "--no-yaml") yaml = false;
+    else if (a == "--rendezvous-selftest") rdv_selftest = true;
     else {
       fprintf(stderr, "usage: miniaero [--input FILE] [--arith fast|strict] [--limiter venkat|vanalbada] [--tile a,b,c] [--precision N] [--yaml DIR] [--no-yaml]\n");
       return a == "--help" || a == "-h" ? 0 : 2;
@@ -98,6 +160,40 @@ int main(int argc, char **argv) {
   const int num_procs = env_int({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE"}, 1);
   const int my_id = env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK"}, 0);
   const int device = env_int({"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK"}, 0);
+
+  if (rdv_selftest) {
+    // the rendezvous alone (no GPU, no NCCL): rank 0 publishes a fresh random token, every rank prints the one it got
+    unsigned char tok[MA_COMM_ID_BYTES];
+    if (my_id == 0) {
+      std::random_device rd;
+      for (unsigned char &b : tok) b = (unsigned char)rd();
+    }
+    if (!exchange_bytes(my_id, num_procs, tok, sizeof(tok), rendezvous_path())) {
+      fprintf(stderr, "miniaero: rank %d: rendezvous failed\n", my_id);
+      return 1;
+    }
+    unsigned long long h = 1469598103934665603ull;
+    for (unsigned char b : tok) h = (h ^ b) * 1099511628211ull;
+    fprintf(stdout, "rendezvous rank %d token %016llx\n", my_id, h);
+    fflush(stdout);
+    if (my_id == 0) {  // stand-in for ncclCommInitRank's rendezvous: wait until the other ranks say they have read it
+      const std::string ack = rendezvous_path() + ".ack";
+      for (int r = 1; r < num_procs; ++r) {
+        bool seen = false;
+        for (int tries = 0; tries < 600 && !seen; ++tries) {
+          seen = access((ack + std::to_string(r)).c_str(), F_OK) == 0;
+          if (!seen) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        }
+        unlink((ack + std::to_string(r)).c_str());
+      }
+      remove_rendezvous_file();
+    } else {
+      const std::string ack = rendezvous_path() + ".ack" + std::to_string(my_id);
+      const int fd = open(ack.c_str(), O_WRONLY | O_CREAT | O_NOFOLLOW, 0600);
+      if (fd >= 0) close(fd);
+    }
+    return 0;
+  }
 
   ma_options opt;
   if (ma_options_read(input.c_str(), &opt)) die("reading the options file");  // Main.C:73-74
@@ -114,11 +210,12 @@ int main(int argc, char **argv) {
   ma_comm *comm = nullptr;
   if (num_procs > 1) {
     unsigned char id[MA_COMM_ID_BYTES];
-    if (!exchange_id(my_id, id)) {
+    if (!exchange_id(my_id, num_procs, id)) {
       fprintf(stderr, "miniaero: rank %d could not obtain the NCCL id (%s)\n", my_id, ma_last_error());
       return 1;
     }
     if (ma_comm_create(id, num_procs, my_id, device, &comm)) die("communicator");
+    remove_rendezvous_file();  // every rank has read it by now
   }
   ma_solver_config cfg;
   ma_solver_config_default(&cfg);

@@ -68,6 +68,7 @@ int dev_alloc(T **p, size_t n, size_t *tally) {
   *p = nullptr;
   if (n == 0) return MA_OK;
   cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess) (void)cudaGetLastError();  // the failure is reported here: do not leave it as the sticky "last error"
   if (e != cudaSuccess)
     return ma_set_error(e == cudaErrorMemoryAllocation ? MA_ERR_NOMEM : MA_ERR_CUDA,
                         std::string("cudaMalloc of ") + std::to_string(n * sizeof(T)) + " bytes: " + cudaGetErrorString(e));
@@ -343,22 +344,31 @@ int one_step(ma_solver *S, const Api &K) {
   if (!S->step_graph[par]) {
     const long long before = S->tm.kernel_launches;
     cudaGraph_t g = nullptr;
-    MA_CUDA_TRY(cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal));
+    // a stream that cannot be captured (the legacy default stream, a stream already capturing) is handled like any
+    // other capture failure: direct launches from now on
+    const cudaError_t be = cudaStreamBeginCapture(S->st, cudaStreamCaptureModeThreadLocal);
     int rc = MA_OK;
-    for (int k = 0; k < 4 && !rc; ++k) rc = run_stage(S, K, k);
-    const cudaError_t ce = cudaStreamEndCapture(S->st, &g);
+    cudaError_t ce = be;
+    if (be == cudaSuccess) {
+      for (int k = 0; k < 4 && !rc; ++k) rc = run_stage(S, K, k);
+      ce = cudaStreamEndCapture(S->st, &g);
+    }
     S->step_graph_launches = S->tm.kernel_launches - before;
     S->tm.kernel_launches = before;
+    S->vcur = par;  // nothing ran during the capture: the stage buffers are where they were
     if (rc || ce != cudaSuccess || !g) {  // capture not possible here: fall back to direct launches for good
       if (g) cudaGraphDestroy(g);
       cudaGetLastError();
       S->use_graph = false;
-      if (rc) return rc;
       for (int k = 0; k < 4; ++k) {
         rc = run_stage(S, K, k);
-        if (rc) return rc;
+        if (rc) break;
       }
-      return MA_OK;
+      if (rc) {  // the step did not happen
+        S->sim_time -= S->opt.dt;
+        S->time_it--;
+      }
+      return rc;
     }
     const cudaError_t ie = cudaGraphInstantiate(&S->step_graph[par], g, 0);
     cudaGraphDestroy(g);
@@ -402,6 +412,54 @@ int download_field(ma_solver *S, const double *soa, int ncomp, double *host) {
 
 }  // namespace
 
+// staging buffers, streams and events of ma_solver_submit; all or nothing (pipe_release undoes a partial set-up)
+static int pipe_setup(ma_solver *S, size_t elems) {
+  ma_solver::Pipe &P = S->pipe;
+  if (!P.cin) MA_CUDA_TRY(cudaStreamCreateWithFlags(&P.cin, cudaStreamNonBlocking));
+  if (!P.cout) MA_CUDA_TRY(cudaStreamCreateWithFlags(&P.cout, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    double **bufs[2] = {&P.d_in[i], &P.d_out[i]};
+    for (double **b : bufs) {
+      if (*b) continue;
+      int rc = dev_alloc(b, elems, &S->device_bytes);
+      if (rc) return rc;
+    }
+    cudaEvent_t *evs[4] = {&P.in_ready[i], &P.in_free[i], &P.out_ready[i], &P.out_free[i]};
+    for (cudaEvent_t *e : evs)
+      if (!*e) MA_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  P.ready = true;
+  return MA_OK;
+}
+static void pipe_release(ma_solver *S) {
+  ma_solver::Pipe &P = S->pipe;
+  const size_t bytes = (size_t)S->n_owned * 5 * sizeof(double);
+  if (P.cin) cudaStreamSynchronize(P.cin);
+  if (P.cout) cudaStreamSynchronize(P.cout);
+  for (int i = 0; i < 2; ++i) {
+    double **bufs[2] = {&P.d_in[i], &P.d_out[i]};
+    for (double **b : bufs)
+      if (*b) {
+        cudaFree(*b);
+        *b = nullptr;
+        S->device_bytes -= bytes;
+      }
+    cudaEvent_t *evs[4] = {&P.in_ready[i], &P.in_free[i], &P.out_ready[i], &P.out_free[i]};
+    for (cudaEvent_t *e : evs)
+      if (*e) {
+        cudaEventDestroy(*e);
+        *e = nullptr;
+      }
+  }
+  if (P.cin) cudaStreamDestroy(P.cin);
+  if (P.cout) cudaStreamDestroy(P.cout);
+  P.cin = P.cout = nullptr;
+  P.ready = false;
+  P.submitted = 0;
+  (void)cudaGetLastError();
+}
+
+
 extern "C" {
 
 void ma_solver_config_default(ma_solver_config *cfg) {
@@ -434,19 +492,9 @@ void ma_solver_destroy(ma_solver *S) {
     if (pp.a) cudaEventDestroy(pp.a);
     if (pp.b) cudaEventDestroy(pp.b);
   }
-  if (S->pipe.cin) cudaStreamSynchronize(S->pipe.cin);
-  if (S->pipe.cout) cudaStreamSynchronize(S->pipe.cout);
   for (int i = 0; i < 2; ++i)
     if (S->step_graph[i]) cudaGraphExecDestroy(S->step_graph[i]);
-  for (int i = 0; i < 2; ++i) {
-    if (S->pipe.d_in[i]) cudaFree(S->pipe.d_in[i]);
-    if (S->pipe.d_out[i]) cudaFree(S->pipe.d_out[i]);
-    cudaEvent_t pe[] = {S->pipe.in_ready[i], S->pipe.in_free[i], S->pipe.out_ready[i], S->pipe.out_free[i]};
-    for (cudaEvent_t e : pe)
-      if (e) cudaEventDestroy(e);
-  }
-  if (S->pipe.cin) cudaStreamDestroy(S->pipe.cin);
-  if (S->pipe.cout) cudaStreamDestroy(S->pipe.cout);
+  pipe_release(S);
   if (S->own_cs && S->cs) cudaStreamDestroy(S->cs);
   if (S->own_stream && S->st) cudaStreamDestroy(S->st);
   delete S;
@@ -629,7 +677,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   const int tile_class = S->strict ? -1 : ma_fast::pick_tile_class(L.max_tile_cells_real, L.max_tile_faces, L.max_tile_halo);
   const int grad_variant =
       (tile_class >= 0 && !(gv && !strcmp(gv, "gather")) && cfg.limiter == MA_LIMITER_VENKAT) ? 1 : 0;
-  const int flux_variant = (tile_class >= 0 && !(fv && !strcmp(fv, "gather"))) ? 1 : 0;
+  const int flux_variant = (tile_class < 0 || (fv && !strcmp(fv, "gather"))) ? 0 : 1;
   // the global face -> cell lists are read by the gather kernels only (the staged kernels use the 16-bit tile-local
   // connectivity): 29 bytes per cell that the default FAST configuration does not spend
   if (S->strict || grad_variant == 0 || flux_variant == 0) {
@@ -699,7 +747,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
     }
     MA_CU(K.prepare(m, (int)gather_smem));
     if (cfg.block_threads <= 0 && !strict) {
-      S->flux_threads = m.flux_variant == 1 ? ma_fast::tile_class_threads(m.tile_class, 1) : 256;
+      S->flux_threads = m.flux_variant >= 1 ? ma_fast::tile_class_threads(m.tile_class, 1) : 256;
       S->grad_threads = 128;
     }
   }
@@ -809,19 +857,11 @@ int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, in
   ma_solver::Pipe &P = S->pipe;
   const size_t elems = (size_t)S->n_owned * 5;
   if (!P.ready) {
-    MA_CUDA_TRY(cudaStreamCreateWithFlags(&P.cin, cudaStreamNonBlocking));
-    MA_CUDA_TRY(cudaStreamCreateWithFlags(&P.cout, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      int rc = dev_alloc(&P.d_in[i], elems, &S->device_bytes);
-      if (rc) return rc;
-      rc = dev_alloc(&P.d_out[i], elems, &S->device_bytes);
-      if (rc) return rc;
-      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.in_ready[i], cudaEventDisableTiming));
-      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.in_free[i], cudaEventDisableTiming));
-      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.out_ready[i], cudaEventDisableTiming));
-      MA_CUDA_TRY(cudaEventCreateWithFlags(&P.out_free[i], cudaEventDisableTiming));
+    int rc = pipe_setup(S, elems);
+    if (rc) {
+      pipe_release(S);  // a failed set-up (typically out of memory) leaves the solver as it was
+      return rc;
     }
-    P.ready = true;
   }
   const Api K = api_of(S->strict);
   const int slot = (int)(P.submitted & 1);

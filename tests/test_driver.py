@@ -100,3 +100,58 @@ def test_driver_without_output_uses_the_structured_constructor(lib, tmp_path):
     assert "Device Run time" in p.stdout and "Setup time" in p.stdout and "4096 cells x 3 steps" in p.stdout
     assert not os.path.exists(tmp_path / "results.0")
     assert len([f for f in os.listdir(tmp_path) if f.endswith(".yaml")]) == 1
+
+
+def _launch_ranks(args, n, cwd, env_extra=None, timeout=600):
+    """n ranks of the driver started by this process (they share a parent, like the ranks of one torchrun agent)."""
+    procs = []
+    for r in range(n):
+        env = dict(os.environ, WORLD_SIZE=str(n), RANK=str(r), LOCAL_RANK=str(r), MASTER_PORT="29517")
+        env.pop("MINIAERO_RENDEZVOUS", None)
+        env.update(env_extra or {})
+        procs.append(subprocess.Popen([EXE] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    return [(p.wait(timeout=timeout), *p.communicate()) for p in procs]
+
+
+def test_rendezvous_survives_a_second_launch_and_a_stale_file(lib, tmp_path):
+    """The NCCL-id rendezvous of the multi-rank driver (no GPU needed: --rendezvous-selftest exchanges a random token
+    the same way).  Two launches in a row with the same MASTER_PORT must each agree on their OWN token, a stale file
+    of an earlier aborted launch must not be read, and nothing may be left behind in /tmp."""
+    assert os.path.isfile(EXE)
+    stale = "/tmp/miniaero_rdv.29517.%d" % os.getpid()
+    with open(stale, "wb") as f:
+        f.write(b"\x55" * 128)          # what an aborted earlier launch of the same parent would leave
+    tokens = []
+    for _ in range(2):
+        out = _launch_ranks(["--rendezvous-selftest"], 2, tmp_path, timeout=120)
+        assert all(rc == 0 for rc, _, _ in out), out
+        toks = {re.search(r"token ([0-9a-f]{16})", so).group(1) for _, so, _ in out}
+        assert len(toks) == 1, out       # both ranks hold rank 0's token of THIS launch
+        tokens.append(toks.pop())
+    stale_hash = 1469598103934665603
+    for b in b"\x55" * 128:
+        stale_hash = ((stale_hash ^ b) * 1099511628211) % (1 << 64)
+    assert tokens[0] != tokens[1] and "%016x" % stale_hash not in tokens
+    assert not [f for f in os.listdir("/tmp") if f.startswith("miniaero_rdv.29517.%d" % os.getpid())]
+
+
+@pytest.mark.gpu
+def test_two_rank_driver_twice(lib, tmp_path):
+    """Two launches of the 2-rank driver back to back (same port): each builds its own communicator and reproduces
+    the reference's MPI build per rank (tests/golden/par_sod_o2_visc_2.npz) at the FAST tolerance."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    inp = dict(cases.PARALLEL["sod_o2_visc"][0], output_results=1)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "par_sod_o2_visc_2.npz"))
+    for launch in range(2):
+        d = tmp_path / ("launch%d" % launch)
+        d.mkdir()
+        _write_inp(d / "miniaero.inp", inp)
+        out = _launch_ranks(["--precision", "17", "--no-yaml"], 2, d)
+        assert all(rc == 0 for rc, _, _ in out), out
+        for r in range(2):
+            res = np.loadtxt(d / ("results.%d" % r))
+            ref = g["r%d_step%d" % (r, inp["ntimesteps"])]
+            linf, l2 = parity.field_errors(res[:, 3:], ref)
+            assert linf <= parity.TOL_100_STEPS and l2 <= parity.TOL_100_STEPS

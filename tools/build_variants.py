@@ -19,6 +19,8 @@ OLD = ["-DMA_C128_FB=3", "-DMA_FLUX_RK_STAGED=1", "-DMA_FLUX_XC=1"]   # the conf
 VARIANTS = {
     # tag: extra -D flags (defaults: 128 threads x 4 CTAs per SM, RK operands read directly, no staged second record)
     "default": [],
+    "pipe": [],                                    # + MINIAERO_FLUX_KERNEL=pipe at run time (tools/experiments/flux_pipe.cuh)
+    "pg1": ["-DMA_PIPE_GATHER=1"],
     "t128b3": OLD,
     "t160b3": ["-DMA_C128_FT=160"] + OLD,
     "t192b3": ["-DMA_C128_FT=192"] + OLD,
@@ -39,14 +41,44 @@ VARIANTS = {
 }
 
 
+EXPERIMENT_TAGS = ("x", "pg", "pipe")   # variants that need tools/experiments/*.patch applied to a copy of csrc/
+
+
+def experiment_sources():
+    """A scratch copy of csrc/ with the timing-experiment branches (MA_FLUX_EXPERIMENT / MA_GRAD_EXPERIMENT) and the
+    pipelined flux kernel (MINIAERO_FLUX_KERNEL=pipe) patched back in: they are kept out of the product sources."""
+    import shutil
+    dst = os.path.join(B.BUILD, "experiment_src")
+    shutil.rmtree(dst, ignore_errors=True)
+    shutil.copytree(B.CSRC, dst)
+    exp = os.path.join(ROOT, "tools", "experiments")
+    shutil.copy(os.path.join(exp, "flux_pipe.cuh"), dst)
+    for patch, target in (("timing_and_pipe_experiments.patch", "kernels.cu"), ("solver_pipe_variant.patch", "solver.cu")):
+        p = subprocess.run(["patch", "-s", os.path.join(dst, target), os.path.join(exp, patch)], capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("tools/experiments/%s no longer applies to csrc/%s (regenerate it): %s" % (patch, target, p.stdout + p.stderr))
+    return dst
+
+
 def build_one(tag):
     out_dir = os.path.join(B.HERE, "variants")
     os.makedirs(out_dir, exist_ok=True)
     obj = os.path.join(B.BUILD, "kernels_fast_%s.o" % tag)
     lib = os.path.join(out_dir, "libminiaero_b200_%s.so" % tag)
     nvcc = B._nvcc()
-    p = subprocess.run([nvcc] + B.ARCH + B.NVCC_COMMON + ["-Xptxas", "-v", "-fmad=true"] + VARIANTS[tag] +
-                       ["-c", os.path.join(B.CSRC, "kernels.cu"), "-o", obj], capture_output=True, text=True)
+    csrc = B.CSRC
+    extra_objs = {}
+    if tag.startswith(EXPERIMENT_TAGS):
+        csrc = EXP_SRC[0]
+        sobj = os.path.join(B.BUILD, "solver_exp.o")
+        common = [a.replace(B.CSRC, csrc) for a in B.NVCC_COMMON]
+        p = subprocess.run([nvcc] + B.ARCH + common + ["-c", os.path.join(csrc, "solver.cu"), "-o", sobj], capture_output=True, text=True)
+        if p.returncode != 0:
+            return tag, p.stderr[-2000:]
+        extra_objs["solver.o"] = sobj
+    common = [a.replace(B.CSRC, csrc) for a in B.NVCC_COMMON]
+    p = subprocess.run([nvcc] + B.ARCH + common + ["-Xptxas", "-v", "-fmad=true"] + VARIANTS[tag] +
+                       ["-c", os.path.join(csrc, "kernels.cu"), "-o", obj], capture_output=True, text=True)
     if p.returncode != 0:
         return tag, p.stderr[-2000:]
     info = []
@@ -54,8 +86,8 @@ def build_one(tag):
     for i, ln in enumerate(lines):
         if "Function properties" in ln and "flux_rk_tma_kernelILb1ELb1ENS_7TileCapILi128" in ln:
             info = [lines[i + 1].strip(), lines[i + 2].strip()]
-    objs = [obj] + [os.path.join(B.BUILD, n) for n in ("kernels_strict.o", "geom_kernels.o", "solver.o", "host_common.o", "host_mesh.o",
-                                                        "layout.o", "comm.o", "host_report.o")]
+    objs = [obj] + [extra_objs.get(n, os.path.join(B.BUILD, n)) for n in ("kernels_strict.o", "geom_kernels.o", "solver.o", "host_common.o",
+                                                                        "host_mesh.o", "layout.o", "comm.o", "host_report.o")]
     p = subprocess.run([nvcc] + B.ARCH + ["-shared", "-o", lib] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl"],
                        capture_output=True, text=True)
     if p.returncode != 0:
@@ -63,9 +95,13 @@ def build_one(tag):
     return tag, " | ".join(info)
 
 
+EXP_SRC = [None]
+
 if __name__ == "__main__":
     B.build()
     tags = sys.argv[1:] or list(VARIANTS)
+    if any(t.startswith(EXPERIMENT_TAGS) for t in tags):
+        EXP_SRC[0] = experiment_sources()
     with ThreadPoolExecutor(max_workers=4) as ex:
         for tag, msg in ex.map(build_one, tags):
             print(tag, "::", msg, flush=True)
