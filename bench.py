@@ -15,6 +15,8 @@ Workloads (all inputs are generated in code, data = "synthetic
                PER GPU (BASELINE configs[3] restricted to N GPUs; at N = 1 it is configs[1]'s mesh with the
                viscous term on: the "full second-order viscous RK4 step" of the north star).  DEFAULT.
   sod_o2       BASELINE configs[1]: the same mesh, second order, inviscid.
+  sod_o1       BASELINE configs[0]'s physics (first-order inviscid Roe, TimeSolverExplicitRK4.h:402-426
+               <false, roe_flux, no_viscous_flux>) on the same mesh: one kernel per stage, 1 928 algorithmic bytes.
   flatplate    BASELINE configs[2]: viscous flat plate 1024x512x128 (NoSlip/Inflow/Tangent/Extrapolate).
   flatplate_strong  BASELINE configs[4]: the flat plate on a fixed 1024x512x512 global mesh split over the N GPUs
                ("scaling": "strong"; not part of the default run).
@@ -47,11 +49,12 @@ WEAK_DIMS = {1: (512, 512, 256), 2: (1024, 512, 256), 4: (1024, 1024, 256), 8: (
 
 def workload_options(name, n_gpus, cells=None):
     """-> dict of miniaero.inp values (Options.h:91-99) for `name` on n_gpus GPUs (weak scaling)."""
-    if name in ("sod_o2_visc", "sod_o2"):
+    if name in ("sod_o2_visc", "sod_o2", "sod_o1"):
         g = cells or WEAK_DIMS[n_gpus]
         # the cell size of the 512x512x256 single-GPU mesh is kept as the mesh grows
         return dict(problem_type=0, lx=0.3048 * g[0] / 512.0, ly=1.0 * g[1] / 512.0, lz=1.0 * g[2] / 256.0, angle=0.0,
-                    nx=g[0], ny=g[1], nz=g[2], dt=5e-7, second_order_space=1, viscous=1 if name == "sod_o2_visc" else 0)
+                    nx=g[0], ny=g[1], nz=g[2], dt=5e-7, second_order_space=0 if name == "sod_o1" else 1,
+                    viscous=1 if name == "sod_o2_visc" else 0)
     if name == "flatplate":
         base = (1024, 512, 128)
         g = cells or tuple(b * s for b, s in zip(base, {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n_gpus]))
@@ -132,10 +135,10 @@ def reference_sample_dims(opt, steps_total, budget_s, cores):
     return best
 
 
-def run_reference(workload, steps, warmup, budget_s, kind="cell", dims=None):
+def run_reference(workload, steps, warmup, budget_s, kind="cell", dims=None, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refrun
-    cores = host_cores()
+    cores = threads or host_cores()
     base = workload_options(workload, 1)
     d = dims or reference_sample_dims(base, steps + warmup, budget_s, cores)
     full = (base["nx"], base["ny"], base["nz"])
@@ -196,20 +199,163 @@ def reference_arm(args):
     sample = ("%s physics on a %dx%dx%d mesh (%d cells), %d warm-up + %d timed RK4 steps, per-step times read from "
               "the Kokkos stand-in's launch log" % (args.workload, r["dims"][0], r["dims"][1], r["dims"][2], r["cells"],
                                                     args.warmup, args.steps))
+    cpu_rec = {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
+               "sample": sample, "cpu": cpu_model(), "top_functors": r["top_functors"]}
+    # the same sample with the reference Makefile's default build (-DATOMICS_FLUX) and on ONE thread (a smaller
+    # sample of the same physics): context for the all-cores figure above
+    few = max(2, min(args.steps, 3))
+    ra = run_reference(args.workload, few, 1, budget_s=args.ref_budget, kind="atomics", dims=tuple(r["dims"]))
+    if ra is not None:
+        cpu_rec["atomics_flux_build"] = {"value": ra["value"], "cores": ra["cores"], "steps": few,
+                                         "what": "reference Makefile default -DATOMICS_FLUX (nondeterministic summation order)"}
+    r1 = run_reference(args.workload, few, 1, budget_s=min(20.0, args.ref_budget), threads=1)
+    if r1 is not None:
+        cpu_rec["one_thread"] = {"value": r1["value"], "cores": 1, "steps": few, "dims": r1["dims"], "cells": r1["cells"]}
     line = {"impl": "reference", "metric": "cell-updates/sec (RK4 steps x cells) FP64", "value": r["value"],
             "unit": "cell-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "cells_per_gpu": opt["nx"] * opt["ny"] * opt["nz"] // max(1, args.gpus),
+            # the mesh this arm actually timed; `sample_of` names the GPU arm's workload it is a bounded sample of
+            "config": {"workload": args.workload, "mesh": list(r["dims"]), "cells": r["cells"],
+                       "sample_of": {"workload": args.workload, "mesh": [opt["nx"], opt["ny"], opt["nz"]],
+                                     "cells_per_gpu": opt["nx"] * opt["ny"] * opt["nz"] // max(1, args.gpus),
+                                     "why": "same physics, cell size and dt on a smaller mesh: the reference's ~5.5 KB per cell and "
+                                            "its serial mesh set-up make the full size impractical on the host, so the two "
+                                            "arms agree in everything but the number of cells"},
                        "second_order": opt["second_order_space"], "viscous": opt["viscous"],
                        "note": "reference = unmodified miniAero sources (-DCELL_FLUX, -O3 -fopenmp) on a Kokkos "
                                "stand-in whose parallel_for is an OpenMP static loop; CPU only"},
-            "cpu_baseline": {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": "reference",
-                             "sample": sample, "cpu": cpu_model(), "top_functors": r["top_functors"]},
+            "cpu_baseline": cpu_rec,
             "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
+
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parity of the very build that is about to be timed (tests/golden/*.npz = full-precision results of the unmodified
+# reference; made by tests/golden/make_golden.py from oracle/_ref, re-derived by tests/test_oracle.py)
+def parity_check(ma, comm, rank, world, local_rank, dist):
+    """Small meshes, 1 / 2 / 100 RK4 steps, per rank against the reference's own results: its serial build at N = 1,
+    its WITH_MPI build on the same block decomposition at N > 1 (CopyGhost.h:93-211, CopyGhost.C:41-79 are what the
+    NCCL halo path replaces).  STRICT arithmetic must be bit-identical, FAST within the north-star tolerance on the
+    global field's scale.  -> dict for the bench line; ok == False fails the run."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases
+    import parity
+    out = {"cases": {}, "tolerance": {"strict_ulp": 0, "fast_per_step": parity.TOL_PER_STEP, "fast_100_steps": parity.TOL_100_STEPS}}
+    names = ["sod_o2_visc"] if world == 1 else [n for n in ("sod_o2_visc", "ramp_o2_visc", "3D_Sod_Parallel")
+                                                if world in cases.PARALLEL[n][1]]
+    worst_ulp, worst_fast, ok = 0, 0.0, True
+    for name in names:
+        if world == 1:
+            inp, g = cases.EXTRA[name], parity.golden(name)
+            key = lambda n: "cell_step%d" % n
+        else:
+            inp = cases.PARALLEL[name][0]
+            g = np.load(os.path.join(parity.GOLDEN, "par_%s_%d.npz" % (name, world)))
+            key = lambda n: "r%d_step%d" % (rank, n)
+        entry = {}
+        for arith, tag in ((ma.ARITH_STRICT, "strict"), (ma.ARITH_FAST, "fast")):
+            for n, tol in ((1, parity.TOL_PER_STEP), (2, 2 * parity.TOL_PER_STEP), (100, parity.TOL_100_STEPS)):
+                opt = ma.Options(**cases.opts_kwargs(dict(inp, ntimesteps=n)))
+                solver = ma.TimeSolverExplicitRK4.from_options(opt, rank, world, device=local_rank, comm=comm, arith=arith)
+                solver.initialize()
+                solver.step(n)
+                sol, ref = solver.solution(), g[key(n)]
+                del solver
+                mine = {"ulp": parity.max_ulp(sol, ref), "parts": parity.field_error_parts(sol, ref)}
+                rows = [mine]
+                if world > 1:
+                    rows = [None] * world
+                    dist.all_gather_object(rows, mine)
+                linf, l2 = parity.combine_parts([r["parts"] for r in rows])
+                ulp = max(r["ulp"] for r in rows)
+                if arith == ma.ARITH_STRICT:
+                    entry["ulp_strict_step%d" % n] = ulp
+                    worst_ulp = max(worst_ulp, ulp)
+                    ok = ok and ulp == 0
+                else:
+                    entry["linf_fast_step%d" % n], entry["l2_fast_step%d" % n] = linf, l2
+                    worst_fast = max(worst_fast, linf / tol, l2 / tol)
+                    ok = ok and linf <= tol and l2 <= tol
+        out["cases"][name] = entry
+    out.update({"ulp_strict": worst_ulp, "fast_error_over_tolerance": worst_fast, "ok": bool(ok), "ranks": world,
+                "reference": "tests/golden/%s (unmodified reference, %s)" % (
+                    "<case>.npz" if world == 1 else "par_<case>_%d.npz" % world,
+                    "-DCELL_FLUX serial build" if world == 1 else "-DCELL_FLUX -DWITH_MPI build, %d ranks" % world)})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host side of the end-to-end leg
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank — and therefore first-touch its pinned buffers — on the cores of its GPU's NUMA node.
+    -> description for the bench line (a box that reports one node for every GPU has nothing to bind)."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if re.fullmatch(r"node\d+", d)]
+        info["numa_nodes"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["bound"], info["cpus"] = True, len(cpus)
+    except Exception as ex:   # no sysfs, no such attribute: nothing to bind
+        info["note"] = str(ex)[:120]
+    return info
+
+
+def host_link_bandwidth(torch, nbytes, barrier, max_over_ranks):
+    """What the box can feed: every rank copies nbytes host->device and device->host between pinned memory and its GPU
+    at the same time (two streams), all ranks together — the pattern of the end-to-end leg.  GB/s per rank and
+    direction, from the slowest rank."""
+    n = int(min(nbytes, 1 << 30)) // 8
+    h_in = torch.empty(n, dtype=torch.float64, pin_memory=True).fill_(1.0)
+    h_out = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    d_in = torch.empty(n, dtype=torch.float64, device="cuda")
+    d_out = torch.ones(n, dtype=torch.float64, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+        best = float("inf")
+        for rep in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            if mode in ("h2d", "both"):
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if mode in ("d2h", "both"):
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+            s1.synchronize(); s2.synchronize()
+            best = min(best, max_over_ranks(time.perf_counter() - t0))
+        res[mode + "_gbs_per_rank"] = (2 if mode == "both" else 1) * n * 8 / best / 1e9
+    res["bytes"] = n * 8
+    return res
+
+
+def source_hash():
+    """Hash of the kernel sources: profiles/traffic.json is only quoted for the build it was measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("kernels.cu", "physics.cuh", "kernels.h"):
+        with open(os.path.join(ROOT, "miniaero_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -306,6 +452,19 @@ def gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    numa = bind_to_gpu_numa_node(local_rank)
+    # ---- parity of this build on this box, before anything is timed (fails the run when it is not met)
+    parity_rec = None
+    if args.parity:
+        parity_rec = parity_check(ma, comm, rank, world, local_rank, dist)
+        if not parity_rec["ok"]:
+            if rank == 0:
+                sys.stderr.write("bench.py: PARITY FAILED, nothing is reported: %s\n" % json.dumps(parity_rec))
+            if world > 1:
+                dist.barrier()
+                dist.destroy_process_group()
+            return 3
+
     cells = tuple(args.cells) if args.cells else None
     optd = workload_options(args.workload, world, cells)
     # host memory gate: the host-side mesh + layout of a 64 M-cell block peaks near 0.9 KB/cell; ranks build in
@@ -340,30 +499,53 @@ def gpu_arm(args):
     dbl2 = DBL_SWEEP2_O2 if second else DBL_SWEEP2_O1
     flux_bytes = 8.0 * dbl2 * n_owned
     achieved = flux_bytes / (flux_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tp):
         with open(tp) as f:
             tj = json.load(f)
         key = "flux_rk_o2" if second else "flux_rk_o1"
-        if key in tj:   # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per owned cell
+        # dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture (tools/measure_traffic.sh), per owned cell;
+        # quoted only for the kernel sources it was captured on
+        if key in tj and tj.get("source_hash") == source_hash():
             traffic = tj[key]["dram_bytes_per_cell"] * n_owned
+            traffic_note = "ncu %s, %s" % (tj.get("captured", "?"), tj.get("recipe", "tools/measure_traffic.sh"))
+        elif key in tj:
+            traffic_note = "profiles/traffic.json was captured on other kernel sources (hash %s, now %s): not quoted" % (
+                tj.get("source_hash"), source_hash())
     bpcu = BYTES_PER_CELL_UPDATE_O2 if (second or optd["viscous"]) else BYTES_PER_CELL_UPDATE_O1
     roofline = {"bound": "hbm", "kernel": "flux_rk_tma_kernel (face fluxes + slot-ordered gather + RK stage update)", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": flux_bytes, "launch_ms": flux_ms,
                 "share_of_step": t["flux_seconds"] / t["step_seconds"],
+                "flux_evaluations_per_cell": t["tile_faces_total"] / float(n_owned),
                 "grad_limiter_kernel": {"launch_ms": grad_ms, "algorithmic_bytes_per_launch": 8.0 * DBL_SWEEP1 * n_owned,
                                         "achieved": (8.0 * DBL_SWEEP1 * n_owned / (grad_ms * 1e-3) / 1e9) if grad_ms > 0 else None,
                                         "frac": (8.0 * DBL_SWEEP1 * n_owned / (grad_ms * 1e-3) / 1e9 / peak) if grad_ms > 0 else None},
                 "whole_step": {"bytes_per_cell_update": bpcu, "achieved": bpcu * (value / world) / 1e9,
                                "frac": bpcu * (value / world) / 1e9 / peak, "frac_of_8TBs_nominal": bpcu * (value / world) / 8e12}}
     launches = int(t["kernel_launches"])
+    halo = None
+    if world > 1:   # what the exchange costs and how much of it the interior tiles hide (max over ranks; rank 0's counts)
+        stages = 4 * args.steps
+        halo = {"exchange_ms_per_stage": 1e3 * max_over_ranks(t["halo_seconds"]) / stages,
+                "exposed_wait_ms_per_stage": 1e3 * max_over_ranks(t["halo_wait_seconds"]) / stages,
+                "exposed_wait_share_of_step": max_over_ranks(t["halo_wait_seconds"]) / step_s,
+                "interior_tiles": int(t["num_interior_tiles"]), "boundary_tiles": int(t["num_tiles"] - t["num_interior_tiles"]),
+                "send_cells": int(t["num_send_cells"]), "recv_cells": int(t["num_recv_cells"]),
+                "bytes_sent_per_stage": int(t["num_send_cells"]) * 25 * 8,
+                "what": "two exchanges per stage on a second stream (stage state 5 doubles, gradient + limiter 20 doubles per "
+                        "ghost): pack kernel, one ncclGroup of send/recv pairs, unpack kernel; exposed wait = time the "
+                        "compute stream stalled before a boundary-tile launch (CUDA events)",
+                "grad_launch_ms": grad_ms, "flux_launch_ms": flux_ms}
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the state from pinned host memory,
     # advances one RK4 step and reads the new state back (ma_solver_set_solution / _step / _get_solution)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     nbytes = n_owned * 5 * 8
+    link = host_link_bandwidth(torch, nbytes, barrier, max_over_ranks)
+    link["numa"] = numa
+    link["concurrent_ranks"] = world
     hin = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
     hout = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
     solver.solution_into(hin.data_ptr())
@@ -400,9 +582,12 @@ def gpu_arm(args):
         finite_pipe = bool(torch.isfinite(houts[0]).all().item() and torch.isfinite(houts[1]).all().item())
         e2e = {"value": total_cells * pipe_steps / pipe_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "steps": pipe_steps, "ms_per_step": 1e3 * pipe_s / pipe_steps,
-               "what": "per step ma_solver_submit(pinned host in, pinned host out, 1): upload of the batch's state, one "
-                       "RK4 step, download of the new state; consecutive independent batches pipelined over three "
-                       "streams (fill and drain of the pipeline inside the timed region)",
+               "what": "INDEPENDENT batches (ensemble members), one per step: ma_solver_submit(pinned host in, pinned host "
+                       "out, 1) = upload of the batch's state, one RK4 step, download of the new state, consecutive batches "
+                       "pipelined over three streams (fill and drain inside the timed region).  A time-stepping user who "
+                       "moves the state across PCIe every step gets `serial_chain` (each step's input is the previous "
+                       "output: nothing can overlap); one who calls Solve() for K steps, as the reference does, gets "
+                       "`solve_call`",
                "result_finite": finite_pipe, "serial_chain": serial}
         del hin2, houts
     except RuntimeError as ex:   # MiniAeroError is a RuntimeError; so is torch's failure to pin host memory
@@ -412,7 +597,7 @@ def gpu_arm(args):
         # the dependent chain is the end-to-end number then
         e2e = {"value": serial["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": nbytes, "steps": serial["steps"], "ms_per_step": serial["ms_per_step"],
-               "what": serial["what"], "pipelined_unavailable": str(ex)[:200]}
+               "what": serial["what"], "pipelined_unavailable": str(ex)[:200], "serial_chain": serial}
     # the reference's own call shape (Main.C:139-141): one Solve() of K steps, state up once, result down once
     barrier()
     w0 = time.perf_counter()
@@ -421,6 +606,15 @@ def gpu_arm(args):
     solve_s = max_over_ranks(time.perf_counter() - w0)
     e2e["solve_call"] = {"value": total_cells * args.steps / solve_s, "steps": args.steps,
                          "what": "one upload + K steps + one download (the reference's Solve() shape)"}
+    # what the host can feed: the per-step traffic of this leg at the copy rates measured above (all ranks at once)
+    both = link["both_gbs_per_rank"] / 2.0   # per direction while both directions run
+    e2e["host_link"] = link
+    e2e["host_link"]["ceiling"] = {
+        "pipelined": total_cells / max(step_s / args.steps, nbytes / (both * 1e9)),
+        "serial_chain": total_cells / (step_s / args.steps + nbytes / (link["h2d_gbs_per_rank"] * 1e9)
+                                       + nbytes / (link["d2h_gbs_per_rank"] * 1e9)),
+        "what": "cell-updates/s if every rank's upload and download ran at the measured pinned-copy rates: pipelined = "
+                "max(device step, transfer at the bidirectional rate); serial = device step + upload + download"}
     finite = bool(torch.isfinite(hout).all().item())
     del hin, hout
 
@@ -429,15 +623,17 @@ def gpu_arm(args):
     if world == 1 and args.also and not args.cells:
         del solver
         torch.cuda.empty_cache()
-        for name in ("sod_o2", "flatplate"):
+        for name in ("sod_o2", "flatplate", "sod_o1"):
             if name == args.workload:
                 continue
             s2, _, i2 = build_solver(ma, workload_options(name, 1), 0, 1, None, local_rank, mesh_path=args.mesh_path)
             t2 = time_steps(s2, max(3, args.steps // 4), 3, barrier)
             v2 = i2["owned_cells"] * t2["steps"] / t2["step_seconds"]
+            b2 = BYTES_PER_CELL_UPDATE_O1 if name == "sod_o1" else BYTES_PER_CELL_UPDATE_O2
             also[name] = {"value": v2, "unit": "cell-updates/s", "steps": int(t2["steps"]), "cells": i2["owned_cells"],
                           "ms_per_step": 1e3 * t2["step_seconds"] / t2["steps"],
-                          "whole_step_roofline_frac": BYTES_PER_CELL_UPDATE_O2 * v2 / 1e9 / peak}
+                          "bytes_per_cell_update": b2, "whole_step_roofline_frac": b2 * v2 / 1e9 / peak,
+                          "flux_launch_ms": 1e3 * t2["flux_seconds"] / (4 * t2["steps"])}
             del s2
         # the bit-for-bit mode (MA_ARITH_STRICT: IEEE evaluation in the reference's order, no FMA, gather kernels), the
         # default workload on a quarter-size mesh: what exact reproduction of the reference's -DCELL_FLUX build costs
@@ -451,6 +647,43 @@ def gpu_arm(args):
                                                 "ms_per_step": 1e3 * t3["step_seconds"] / t3["steps"],
                                                 "what": "MA_ARITH_STRICT: bit for bit the reference's -DCELL_FLUX results"}
             del s3
+
+    # ---- strong scaling (BASELINE configs[4]): the viscous flat plate on a FIXED 1024 x 512 x 512 mesh over the N GPUs
+    strong = None
+    if args.strong and args.workload != "flatplate_strong" and not args.cells:
+        try:
+            del solver
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        so = workload_options("flatplate_strong", world)
+        need = 600.0 * so["nx"] * so["ny"] * so["nz"] / world   # ~575 B/cell of device memory
+        free_dev = torch.cuda.mem_get_info()[0]
+        if need > 0.95 * free_dev:
+            strong = {"skipped": "%.0f GB per GPU needed, %.0f GB free" % (need / 1e9, free_dev / 1e9)}
+        else:
+            per_rank4 = (320.0 if args.mesh_path == "structured" else 900.0) * so["nx"] * so["ny"] * so["nz"] / world
+            group4 = int(max(1, min(world, avail * 0.8 // max(per_rank4, 1.0))))
+            for g0 in range(0, world, group4):
+                if g0 <= rank < g0 + group4:
+                    s4, _, i4 = build_solver(ma, so, rank, world, comm, local_rank, mesh_path=args.mesh_path)
+                barrier()
+            t4 = time_steps(s4, max(3, args.steps // 2), 3, barrier)
+            st4 = max_over_ranks(t4["step_seconds"])
+            cells4 = so["nx"] * so["ny"] * so["nz"]
+            strong = {"workload": "flatplate_strong", "mesh": [so["nx"], so["ny"], so["nz"]], "cells": cells4,
+                      "value": cells4 * t4["steps"] / st4, "unit": "cell-updates/s", "steps": int(t4["steps"]),
+                      "ms_per_step": 1e3 * st4 / t4["steps"], "cells_per_gpu": i4["owned_cells"], "blocks": i4["nproc"],
+                      "setup_seconds": round(i4["layout_upload_seconds"], 2),
+                      "halo_exposed_wait_ms_per_step": 1e3 * max_over_ranks(t4["halo_wait_seconds"]) / t4["steps"]}
+            ref_file = os.path.join(ROOT, "profiles", "strong_scaling.json")
+            if os.path.isfile(ref_file):   # efficiency against the smallest GPU count that holds the mesh (committed line)
+                with open(ref_file) as f:
+                    base = json.load(f).get("base")
+                if base and base.get("value"):
+                    strong["efficiency"] = strong["value"] / (base["value"] * world / base["n_gpus"])
+                    strong["efficiency_vs"] = base
+            del s4
 
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:
@@ -481,7 +714,12 @@ def gpu_arm(args):
                            "setup_seconds": {k: round(v, 2) for k, v in info.items() if k.endswith("_seconds")},
                            "mesh_path": info["mesh_path"]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "wall_ms_per_step": 1e3 * t["wall_seconds"] / args.steps, "result_finite": finite}
+                "wall_ms_per_step": 1e3 * t["wall_seconds"] / args.steps, "result_finite": finite,
+                "parity": parity_rec}
+        if world > 1:
+            line["halo"] = halo
+        if strong is not None:
+            line["strong"] = strong
         if also:
             line["also"] = also
         print(json.dumps(line), flush=True)
@@ -497,18 +735,24 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="sod_o2_visc", choices=["sod_o2_visc", "sod_o2", "flatplate", "flatplate_strong"])
+    ap.add_argument("--workload", default="sod_o2_visc", choices=["sod_o2_visc", "sod_o2", "sod_o1", "flatplate", "flatplate_strong"])
     ap.add_argument("--cells", type=int, nargs=3, default=None, help="override the GLOBAL mesh (debugging only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--mesh-path", default="structured", choices=["structured", "arrays"],
                     help="how the solver is constructed (set-up only; the timed steps are the same kernels)")
     ap.add_argument("--no-also", dest="also", action="store_false")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the parity check of this build")
+    ap.add_argument("--strong", dest="strong", action="store_true", default=None,
+                    help="also time the fixed-size 1024x512x512 flat plate (default: on for N > 1)")
+    ap.add_argument("--no-strong", dest="strong", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--ref-budget", type=float, default=90.0, help="seconds of CPU work for --impl reference")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
+    if args.strong is None:
+        args.strong = args.gpus > 1
     # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version banner, ...)
     # goes to stderr for the duration of the run
     sys.stdout.flush()

@@ -216,6 +216,11 @@ typedef struct ma_timing {
   size_t device_bytes;      /* device memory held by the solver */
   int num_tiles;
   int tile_faces_total;     /* faces summed over tiles (each tile-boundary face counted twice) */
+  /* block-decomposed runs (zero otherwise) */
+  int num_interior_tiles;   /* tiles that touch no ghost cell: they run while the halo exchange is in flight */
+  int num_send_cells, num_recv_cells; /* cells packed / ghosts unpacked per exchange */
+  double halo_wait_seconds; /* time the compute stream sat waiting for an exchange before a boundary-tile launch
+                               (events; 0 when not profiled): the part of halo_seconds that was NOT hidden */
 } ma_timing;
 int ma_solver_get_timing(ma_solver *s, ma_timing *t);
 int ma_solver_reset_timing(ma_solver *s);

@@ -261,6 +261,7 @@ int start_state_exchange(ma_solver *S, double *state) {
 }
 int wait_state_exchange(ma_solver *S) {
   if (S->u_pending) {
+    ProfScope exposed(S, &S->tm.halo_wait_seconds);  // a->b spans exactly the stall of the compute stream
     MA_CUDA_TRY(cudaStreamWaitEvent(S->st, S->ev_u, 0));
     S->u_pending = false;
   }
@@ -309,7 +310,10 @@ int run_stage(ma_solver *S, const Api &K, int k) {
       ProfScope p(S, &S->tm.flux_seconds);
       MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, 0, nint, S->flux_threads, S->st));
       S->tm.kernel_launches += nint > 0;
-      if (S->n_ghost) MA_CUDA_TRY(cudaStreamWaitEvent(S->st, S->ev_gl, 0));
+      if (S->n_ghost) {
+        ProfScope exposed(S, &S->tm.halo_wait_seconds);
+        MA_CUDA_TRY(cudaStreamWaitEvent(S->st, S->ev_gl, 0));
+      }
       MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
       S->tm.kernel_launches += nbnd > 0;
     }
@@ -754,6 +758,9 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   S->tm.device_bytes = S->device_bytes;
   S->tm.num_tiles = S->n_tiles;
   S->tm.tile_faces_total = (int)std::min<long>(L.n_tile_faces_real, 2147483647L);
+  S->tm.num_interior_tiles = S->n_ghost ? S->n_interior_tiles : S->n_tiles;
+  S->tm.num_send_cells = S->n_send;
+  S->tm.num_recv_cells = S->n_recv;
   MA_CU(cudaDeviceSynchronize());
 #undef MA_TRY
 #undef MA_CU
@@ -951,7 +958,7 @@ int ma_solver_get_timing(ma_solver *S, ma_timing *t) {
 
 int ma_solver_reset_timing(ma_solver *S) {
   if (!S) return ma_set_error(MA_ERR_INVALID, "null solver");
-  S->tm.step_seconds = S->tm.grad_seconds = S->tm.flux_seconds = S->tm.halo_seconds = 0.0;
+  S->tm.step_seconds = S->tm.grad_seconds = S->tm.flux_seconds = S->tm.halo_seconds = S->tm.halo_wait_seconds = 0.0;
   S->tm.steps = S->tm.cell_updates = S->tm.kernel_launches = 0;
   return MA_OK;
 }

@@ -11,6 +11,8 @@
 #   miniAero.atomics.omp -DATOMICS_FLUX   -fopenmp
 #   miniAero.cell.mpi    -DCELL_FLUX -DWITH_MPI=1 over oracle/mpi_standin (N cooperating processes)
 #   miniAero.cell.vanalbada  -DCELL_FLUX with the stencil limiter redirected to VanAlbadaLimiter (oracle/vanalbada_swap.h)
+#   miniAero.b200        the reference's Main.C + mesh generator, solver class = include/reference_binding/TimeSolverB200.h
+#                        (links libminiaero_b200.so: the compiled proof that the C ABI is a drop-in; GPU needed to run)
 #   unit_oracle          oracle/unit_oracle.cpp: the reference's device functions (Roe, viscous, primitives, limiters)
 #                        included from the reference headers and evaluated on arrays of inputs
 set -euo pipefail
@@ -48,6 +50,25 @@ if [ ! "$VA" -nt "$HERE/vanalbada_swap.h" ] || [ ! "$VA" -nt "$HERE/kokkos_stand
    g++ $COMMON -DCELL_FLUX "$TMPO/Main.o" ${SRCS#Main.C } -o "$VA")
   rm -rf "$TMPO"
   echo "built $VA"
+fi
+# the reference's own Main.C / mesh generator with its solver class replaced by the B200 drop-in
+# (include/reference_binding/: the binding a maintainer would add; tests/test_reference_binding.py runs it on the GPU)
+ROOT="$(cd "$HERE/.." && pwd)"
+B2="$OUT/miniAero.b200"
+LIBDIR="$ROOT/miniaero_b200"
+if [ -f "$LIBDIR/libminiaero_b200.so" ]; then
+  if [ ! "$B2" -nt "$ROOT/include/reference_binding/TimeSolverB200.h" ] || [ ! "$B2" -nt "$ROOT/include/reference_binding/use_b200_solver.h" ] \
+     || [ ! "$B2" -nt "$ROOT/include/miniaero_b200.h" ] || [ ! "$B2" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ] || [ ! "$B2" -nt "$HERE/build_ref.sh" ]; then
+    TMPO="$(mktemp -d)"
+    (cd "$REF" && g++ $COMMON -DCELL_FLUX -I"$ROOT/include" -I"$ROOT/include/reference_binding" \
+        -include "$ROOT/include/reference_binding/use_b200_solver.h" -c Main.C -o "$TMPO/Main.o" &&
+     g++ $COMMON -DCELL_FLUX "$TMPO/Main.o" ${SRCS#Main.C } -o "$B2" -L"$LIBDIR" -lminiaero_b200 \
+        -Wl,-rpath,'$ORIGIN/../../miniaero_b200')
+    rm -rf "$TMPO"
+    echo "built $B2"
+  fi
+else
+  echo "build_ref.sh: $LIBDIR/libminiaero_b200.so not built yet: skipping miniAero.b200"
 fi
 # unit oracle: a driver of ours around the reference's headers (no reference source is copied)
 if [ ! "$OUT/unit_oracle" -nt "$HERE/unit_oracle.cpp" ] || [ ! "$OUT/unit_oracle" -nt "$HERE/kokkos_standin/Kokkos_Core.hpp" ]; then
