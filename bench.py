@@ -541,82 +541,84 @@ def gpu_arm(args):
 
     # ---- end to end through the C ABI with HOST buffers: every step uploads the state from pinned host memory,
     # advances one RK4 step and reads the new state back (ma_solver_set_solution / _step / _get_solution)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    nbytes = n_owned * 5 * 8
-    link = host_link_bandwidth(torch, nbytes, barrier, max_over_ranks)
-    link["numa"] = numa
-    link["concurrent_ranks"] = world
-    hin = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
-    hout = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
-    solver.solution_into(hin.data_ptr())
-    for _ in range(2):   # warm-up (allocates the device staging buffer)
-        solver.set_solution(hin.data_ptr()); solver.step(1); solver.solution_into(hout.data_ptr())
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        solver.set_solution(hin.data_ptr())
-        solver.step(1)
-        solver.solution_into(hout.data_ptr())   # synchronises the solver's stream
-        hin, hout = hout, hin
-    solver.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - w0)
-    serial = {"value": total_cells * e2e_steps / e2e_s, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-              "what": "dependent chain, nothing overlapped: per step ma_solver_set_solution(pinned host) + "
-                      "ma_solver_step(1) + ma_solver_get_solution(pinned host), each step's input = the previous output"}
-    # The same three operations per step through ma_solver_submit: every step is an independent batch (its own
-    # pinned input state, its own pinned output), so the upload of batch i+1 and the download of batch i-1 run on
-    # their own streams while batch i is stepped.  Two input states (the solution at two different times) alternate.
-    pipe_steps = max(args.steps, e2e_steps)
-    try:
-        for _ in range(2):   # warm-up (allocates the device staging buffers: four more copies of the state)
-            solver.submit(hin.data_ptr(), hout.data_ptr(), 1)
-        solver.synchronize()
-        hin2 = hout.clone().pin_memory()
-        houts = [hout, torch.empty_like(hout).pin_memory()]
+    e2e, finite = None, True
+    if args.e2e_steps > 0:   # (0: a diagnostic run without the end-to-end legs and their host / device buffers)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        nbytes = n_owned * 5 * 8
+        link = host_link_bandwidth(torch, nbytes, barrier, max_over_ranks)
+        link["numa"] = numa
+        link["concurrent_ranks"] = world
+        hin = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
+        hout = torch.empty(n_owned * 5, dtype=torch.float64, pin_memory=True)
+        solver.solution_into(hin.data_ptr())
+        for _ in range(2):   # warm-up (allocates the device staging buffer)
+            solver.set_solution(hin.data_ptr()); solver.step(1); solver.solution_into(hout.data_ptr())
         barrier()
         w0 = time.perf_counter()
-        for i in range(pipe_steps):
-            solver.submit((hin, hin2)[i & 1].data_ptr(), houts[i & 1].data_ptr(), 1)
+        for _ in range(e2e_steps):
+            solver.set_solution(hin.data_ptr())
+            solver.step(1)
+            solver.solution_into(hout.data_ptr())   # synchronises the solver's stream
+            hin, hout = hout, hin
         solver.synchronize()
-        pipe_s = max_over_ranks(time.perf_counter() - w0)
-        finite_pipe = bool(torch.isfinite(houts[0]).all().item() and torch.isfinite(houts[1]).all().item())
-        e2e = {"value": total_cells * pipe_steps / pipe_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes, "steps": pipe_steps, "ms_per_step": 1e3 * pipe_s / pipe_steps,
-               "what": "INDEPENDENT batches (ensemble members), one per step: ma_solver_submit(pinned host in, pinned host "
-                       "out, 1) = upload of the batch's state, one RK4 step, download of the new state, consecutive batches "
-                       "pipelined over three streams (fill and drain inside the timed region).  A time-stepping user who "
-                       "moves the state across PCIe every step gets `serial_chain` (each step's input is the previous "
-                       "output: nothing can overlap); one who calls Solve() for K steps, as the reference does, gets "
-                       "`solve_call`",
-               "result_finite": finite_pipe, "serial_chain": serial}
-        del hin2, houts
-    except RuntimeError as ex:   # MiniAeroError is a RuntimeError; so is torch's failure to pin host memory
-        if "memory" not in str(ex).lower() and "cudaMalloc" not in str(ex):
-            raise
-        # no room for the pipeline's staging buffers next to a solver that fills the device (every rank sizes alike):
-        # the dependent chain is the end-to-end number then
-        e2e = {"value": serial["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": nbytes, "steps": serial["steps"], "ms_per_step": serial["ms_per_step"],
-               "what": serial["what"], "pipelined_unavailable": str(ex)[:200], "serial_chain": serial}
-    # the reference's own call shape (Main.C:139-141): one Solve() of K steps, state up once, result down once
-    barrier()
-    w0 = time.perf_counter()
-    solver.set_solution(hin.data_ptr()); solver.step(args.steps); solver.solution_into(hout.data_ptr())
-    solver.synchronize()
-    solve_s = max_over_ranks(time.perf_counter() - w0)
-    e2e["solve_call"] = {"value": total_cells * args.steps / solve_s, "steps": args.steps,
-                         "what": "one upload + K steps + one download (the reference's Solve() shape)"}
-    # what the host can feed: the per-step traffic of this leg at the copy rates measured above (all ranks at once)
-    both = link["both_gbs_per_rank"] / 2.0   # per direction while both directions run
-    e2e["host_link"] = link
-    e2e["host_link"]["ceiling"] = {
-        "pipelined": total_cells / max(step_s / args.steps, nbytes / (both * 1e9)),
-        "serial_chain": total_cells / (step_s / args.steps + nbytes / (link["h2d_gbs_per_rank"] * 1e9)
-                                       + nbytes / (link["d2h_gbs_per_rank"] * 1e9)),
-        "what": "cell-updates/s if every rank's upload and download ran at the measured pinned-copy rates: pipelined = "
-                "max(device step, transfer at the bidirectional rate); serial = device step + upload + download"}
-    finite = bool(torch.isfinite(hout).all().item())
-    del hin, hout
+        e2e_s = max_over_ranks(time.perf_counter() - w0)
+        serial = {"value": total_cells * e2e_steps / e2e_s, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                  "what": "dependent chain, nothing overlapped: per step ma_solver_set_solution(pinned host) + "
+                          "ma_solver_step(1) + ma_solver_get_solution(pinned host), each step's input = the previous output"}
+        # The same three operations per step through ma_solver_submit: every step is an independent batch (its own
+        # pinned input state, its own pinned output), so the upload of batch i+1 and the download of batch i-1 run on
+        # their own streams while batch i is stepped.  Two input states (the solution at two different times) alternate.
+        pipe_steps = max(args.steps, e2e_steps)
+        try:
+            for _ in range(2):   # warm-up (allocates the device staging buffers: four more copies of the state)
+                solver.submit(hin.data_ptr(), hout.data_ptr(), 1)
+            solver.synchronize()
+            hin2 = hout.clone().pin_memory()
+            houts = [hout, torch.empty_like(hout).pin_memory()]
+            barrier()
+            w0 = time.perf_counter()
+            for i in range(pipe_steps):
+                solver.submit((hin, hin2)[i & 1].data_ptr(), houts[i & 1].data_ptr(), 1)
+            solver.synchronize()
+            pipe_s = max_over_ranks(time.perf_counter() - w0)
+            finite_pipe = bool(torch.isfinite(houts[0]).all().item() and torch.isfinite(houts[1]).all().item())
+            e2e = {"value": total_cells * pipe_steps / pipe_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+                   "d2h_bytes_per_step": nbytes, "steps": pipe_steps, "ms_per_step": 1e3 * pipe_s / pipe_steps,
+                   "what": "INDEPENDENT batches (ensemble members), one per step: ma_solver_submit(pinned host in, pinned host "
+                           "out, 1) = upload of the batch's state, one RK4 step, download of the new state, consecutive batches "
+                           "pipelined over three streams (fill and drain inside the timed region).  A time-stepping user who "
+                           "moves the state across PCIe every step gets `serial_chain` (each step's input is the previous "
+                           "output: nothing can overlap); one who calls Solve() for K steps, as the reference does, gets "
+                           "`solve_call`",
+                   "result_finite": finite_pipe, "serial_chain": serial}
+            del hin2, houts
+        except RuntimeError as ex:   # MiniAeroError is a RuntimeError; so is torch's failure to pin host memory
+            if "memory" not in str(ex).lower() and "cudaMalloc" not in str(ex):
+                raise
+            # no room for the pipeline's staging buffers next to a solver that fills the device (every rank sizes alike):
+            # the dependent chain is the end-to-end number then
+            e2e = {"value": serial["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes,
+                   "d2h_bytes_per_step": nbytes, "steps": serial["steps"], "ms_per_step": serial["ms_per_step"],
+                   "what": serial["what"], "pipelined_unavailable": str(ex)[:200], "serial_chain": serial}
+        # the reference's own call shape (Main.C:139-141): one Solve() of K steps, state up once, result down once
+        barrier()
+        w0 = time.perf_counter()
+        solver.set_solution(hin.data_ptr()); solver.step(args.steps); solver.solution_into(hout.data_ptr())
+        solver.synchronize()
+        solve_s = max_over_ranks(time.perf_counter() - w0)
+        e2e["solve_call"] = {"value": total_cells * args.steps / solve_s, "steps": args.steps,
+                             "what": "one upload + K steps + one download (the reference's Solve() shape)"}
+        # what the host can feed: the per-step traffic of this leg at the copy rates measured above (all ranks at once)
+        both = link["both_gbs_per_rank"] / 2.0   # per direction while both directions run
+        e2e["host_link"] = link
+        e2e["host_link"]["ceiling"] = {
+            "pipelined": total_cells / max(step_s / args.steps, nbytes / (both * 1e9)),
+            "serial_chain": total_cells / (step_s / args.steps + nbytes / (link["h2d_gbs_per_rank"] * 1e9)
+                                           + nbytes / (link["d2h_gbs_per_rank"] * 1e9)),
+            "what": "cell-updates/s if every rank's upload and download ran at the measured pinned-copy rates: pipelined = "
+                    "max(device step, transfer at the bidirectional rate); serial = device step + upload + download"}
+        finite = bool(torch.isfinite(hout).all().item())
+        del hin, hout
 
     # ---- the other single-GPU workloads, a few steps each (N = 1, default workload only)
     also = {}
@@ -743,7 +745,7 @@ def main():
     ap.add_argument("--no-also", dest="also", action="store_false")
     ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the parity check of this build")
     ap.add_argument("--strong", dest="strong", action="store_true", default=None,
-                    help="also time the fixed-size 1024x512x512 flat plate (default: on for N > 1)")
+                    help="also time the fixed-size 1024x512x512 flat plate (default: on; skipped when it does not fit)")
     ap.add_argument("--no-strong", dest="strong", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
@@ -752,7 +754,7 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.strong is None:
-        args.strong = args.gpus > 1
+        args.strong = True
     # stdout carries exactly one JSON line: everything else a library prints there (NCCL's version banner, ...)
     # goes to stderr for the duration of the run
     sys.stdout.flush()
