@@ -537,7 +537,7 @@ MA_DEV void cp_async8s(unsigned dst, const double *gmem_src) {
 //   MA_FLUX_XC                1: the outside record of a thread's second cut face is staged in shared memory
 //   MA_FLUX_PREFETCH_AHEAD    > 0: each CTA bulk-prefetches into L2 the operand runs of the tile that many CTAs ahead
 #ifndef MA_C128_FT
-#define MA_C128_FT 128
+#define MA_C128_FT 160
 #endif
 #ifndef MA_C128_FB
 #define MA_C128_FB 4
@@ -571,7 +571,7 @@ using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
 #ifndef MA_C128_GB1
 #define MA_C128_GB1 4
 #endif
-using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 4x4x8 / 8x4x4 bricks (flux: 16 warps per SM at 124 registers, no spills)
+using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 4x4x8 / 8x4x4 bricks (flux: 160 threads = one per cut face, 464 faces in three rounds; 20 warps per SM at 94 registers, no spills)
 #ifndef MA_C256_FB
 #define MA_C256_FB 1
 #endif
@@ -580,7 +580,7 @@ using Cap256 = TileCap<256, 896, 256, 256, 1, 2, 256, MA_C256_FB>;  // 8x8x4 / 4
 // ---- sweep 1: Green-Gauss gradient + stencil min/max + Venkatakrishnan limiter ----------------------
 // One own cell: neighbours (sV), face normals and centroids (sG) from shared memory; sn[s] = slot_face | slot_nbr << 16
 // GLOBAL_G: the geometry is read from the tile's run in global memory (component stride gstride) instead of the staged copy
-template <bool SECOND, int LS, bool GLOBAL_G>
+template <bool SECOND, int LS, bool GLOBAL_G, bool VANALBADA>
 MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const int gstride, const double *__restrict__ sV, int pos,
                               const unsigned (&sn)[6], double vol, const double (&xc)[3], int c, int stride,
                               double *__restrict__ grad, double *__restrict__ lim) {
@@ -630,7 +630,26 @@ MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const int gstride, 
         grad[(size_t)(k * 3 + d) * stride + c] = g[k][d];
       }
   }
-  if (SECOND) {
+  if (SECOND && VANALBADA) {
+    // VanAlbadaLimiter.h:45-65 in place of VenkatLimiter at StencilLimiter.h:455,459 (the alternative the reference
+    // ships but never calls): phi = min over the six faces, from 1 (StencilLimiter.h:308-311, 345-346)
+    double pva[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
+#pragma unroll 1
+    for (int s = 0; s < 6; ++s) {
+      const int e = (int)(sn[s] & 0x3fffu);
+      double disp[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+        disp[d] = (GLOBAL_G ? __ldg(sG + (3 + d) * gstride + e) : sG[(3 + d) * gstride + e]) - xc[d];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const double dU = fma(disp[2], g[k][2], fma(disp[1], g[k][1], disp[0] * g[k][0]));
+        pva[k] = fmin(pva[k], vanalbada_limit(mx[k] - V[k], mn[k] - V[k], dU));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lim[(size_t)k * stride + c] = pva[k];
+  } else if (SECOND) {
     double pN[5] = {1.0, 1.0, 1.0, 1.0, 1.0}, pD[5] = {1.0, 1.0, 1.0, 1.0, 1.0};
     double dumax[5], ndumin[5];
 #pragma unroll
@@ -672,7 +691,7 @@ MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const int gstride, 
 // GDIRECT (persistent only; MINIAERO_GRAD_PERSIST=2): the face geometry is not staged — a stage is the 12 KB of cell
 // states, so two stages fit under four resident CTAs — but read from the tile's run in global memory by the cell
 // threads, after a bulk L2 prefetch issued one tile ahead.
-template <bool SECOND, class CAP, bool PERSIST, bool GDIRECT = false>
+template <bool SECOND, class CAP, bool PERSIST, bool GDIRECT = false, bool VANALBADA = false>
 __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP::GRAD_MINB : CAP::GRAD_MINB1)
     grad_limiter_tma_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
                             double *__restrict__ lim, int tile_begin, int ntiles) {
@@ -776,12 +795,12 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
     if (tid < T0.cell_count) {
       const double *sG = sbase + st * STAGE, *sV = sG + NG * FC;
       if (GDIRECT)
-        grad_limiter_cell<SECOND, LS, true>(m.face_geom + (size_t)6 * T0.face_start, (int)((unsigned)(T0.face_count + 15) & ~15u),
+        grad_limiter_cell<SECOND, LS, true, VANALBADA>(m.face_geom + (size_t)6 * T0.face_start, (int)((unsigned)(T0.face_count + 15) & ~15u),
                                             sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc, T0.cell_start + tid,
                                             m.stride, grad, lim);
       else
-        grad_limiter_cell<SECOND, LS, false>(sG, FC, sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc,
-                                             T0.cell_start + tid, m.stride, grad, lim);
+        grad_limiter_cell<SECOND, LS, false, VANALBADA>(sG, FC, sV, (T0.cell_start & 1) + tid, cur.sn, cur.vol, cur.xc,
+                                                        T0.cell_start + tid, m.stride, grad, lim);
     }
     if (!has1) break;
     __syncthreads();  // every read of stage st is done before tile i+2 is copied into it
@@ -877,18 +896,19 @@ MA_DEV void face_side(const REC &rec, const double (&xf)[3], const double (&n)[3
 }
 // Roe flux (Roe_Flux.h:49-265) minus the Newtonian viscous flux (Viscous_Flux.h:65-98) at the face state
 // 0.5 (Vl + Vr) (Flux.h:142-143); q = (tau . a, grad T . a) of TWICE the face gradient (both sides' shares summed)
+MA_DEV void subtract_viscous_flux(const double (&Vl)[5], const double (&Vr)[5], const double (&q)[4], double (&flux)[5]) {
+  const double mu = compute_viscosity(0.5 * (Vl[4] + Vr[4]));
+  const double uq = (Vl[1] + Vr[1]) * q[0] + (Vl[2] + Vr[2]) * q[1] + (Vl[3] + Vr[3]) * q[2];
+  flux[1] -= mu * q[0];
+  flux[2] -= mu * q[1];
+  flux[3] -= mu * q[2];
+  flux[4] -= fma(0.5 * mu, uq, 0.5 * compute_thermal_conductivity(mu) * q[3]);
+}
 template <bool VISCOUS>
 MA_DEV void interior_flux(const double (&Vl)[5], const double (&Vr)[5], const double (&q)[4], const FaceGeom &G,
                           double (&flux)[5]) {
   face_roe_flux(Vl, Vr, G, flux);
-  if (VISCOUS) {
-    const double mu = compute_viscosity(0.5 * (Vl[4] + Vr[4]));
-    const double uq = (Vl[1] + Vr[1]) * q[0] + (Vl[2] + Vr[2]) * q[1] + (Vl[3] + Vr[3]) * q[2];
-    flux[1] -= mu * q[0];
-    flux[2] -= mu * q[1];
-    flux[3] -= mu * q[2];
-    flux[4] -= fma(0.5 * mu, uq, 0.5 * compute_thermal_conductivity(mu) * q[3]);
-  }
+  if (VISCOUS) subtract_viscous_flux(Vl, Vr, q, flux);
 }
 
 template <bool SECOND, bool VISCOUS, class CAP>
@@ -1255,7 +1275,25 @@ __global__ void probe_viscous_kernel(int n, const double *g, const double *v, co
     for (int d = 0; d < 3; ++d) G[k][d] = g[15 * i + 3 * k + d];
   }
   for (int d = 0; d < 3; ++d) A[d] = a[3 * i + d];
+#ifdef MA_STRICT
   viscous_flux(G, V, A, F);
+#else
+  // the production path of the FAST face loop (not the reference-shaped viscous_flux, which FAST only uses for the
+  // no-slip wall): the face gradient G = 0.5 (G + G) enters as the two sides' shares of tau.a / gradT.a (face_side),
+  // the face state V = 0.5 (V + V) as the two side states, and subtract_viscous_flux turns them into the flux
+  double rec[20];
+  for (int k = 0; k < 5; ++k) {
+    rec[k] = V[k];
+    for (int d = 0; d < 3; ++d) rec[5 + 3 * k + d] = G[k][d];
+  }
+  const double xf[3] = {0.0, 0.0, 0.0};
+  double Vs[5], q[4];
+  face_side<false, true, true>(RegRecord<false, true>{rec}, xf, A, Vs, q);
+  face_side<false, true, false>(RegRecord<false, true>{rec}, xf, A, Vs, q);
+  for (int k = 0; k < 5; ++k) F[k] = 0.0;
+  subtract_viscous_flux(Vs, Vs, q, F);
+  for (int k = 0; k < 5; ++k) F[k] = -F[k];
+#endif
   for (int k = 0; k < 5; ++k) vf[5 * i + k] = F[k];
 }
 __global__ void probe_primitives_kernel(int n, const double *u, double *v) {
@@ -1361,6 +1399,10 @@ template <class CAP>
 static cudaError_t launch_grad_tma(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
                                    int tile_begin, int ntiles, cudaStream_t st) {
   const size_t smem = grad_tma_smem<CAP>(second);
+  if (second && m.limiter == 1) {  // the alternative limiter: one tile per CTA (the persistent forms are experiments)
+    grad_limiter_tma_kernel<true, CAP, false, false, true><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+    return cudaGetLastError();
+  }
   if (grad_persistent() == 2) {
     const int grid = std::min(ntiles, persistent_ctas(CAP::GRAD_MINB1));
     if (second)
@@ -1409,6 +1451,7 @@ static cudaError_t prepare_tma() {
   MA_SET((grad_limiter_tma_kernel<false, CAP, true>), grad_tma_smem<CAP>(false))
   MA_SET((grad_limiter_tma_kernel<true, CAP, false>), grad_tma_smem<CAP>(true))
   MA_SET((grad_limiter_tma_kernel<false, CAP, false>), grad_tma_smem<CAP>(false))
+  MA_SET((grad_limiter_tma_kernel<true, CAP, false, false, true>), grad_tma_smem<CAP>(true))
   // the direct-geometry gradient variant stages 23 KB per CTA: leave the rest of the SM's array to L1, where the
   // second reader of a face's geometry finds it
   e = cudaFuncSetAttribute((grad_limiter_tma_kernel<true, CAP, true, true>), cudaFuncAttributePreferredSharedMemoryCarveout, 45);

@@ -20,7 +20,7 @@ struct DevMesh {
   int flux_smem_stride;                // per-component stride of the shared-memory face staging (>= faces of a tile)
   int rk_smem_stride;                  // per-component stride of the staged RK operands (>= cells of a tile)
   int grad_variant, flux_variant;      // FAST kernels: 0 = gather kernels, 1 = bulk-copy (TMA) staged tile kernels
-  int limiter;                         // ma_limiter: 0 Venkatakrishnan, 1 Van Albada (gather kernels only)
+  int limiter;                         // ma_limiter: 0 Venkatakrishnan, 1 Van Albada
   int tile_class;                      // capacity class of the staged tile kernels (kernels.cu: TileClass), -1: none fits
   int max_tile_cells, max_tile_faces, max_tile_halo, max_tile_local;
   int halo_stride;                     // tile_halo entries per tile (tile k's list starts at k * halo_stride, -1 padded)

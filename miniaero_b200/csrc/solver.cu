@@ -681,12 +681,11 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
   if (!S->strict) MA_TRY(dev_upload(&S->d_slot_nbr, L.slot_nbr, &S->device_bytes));
   // kernel variants (FAST: the bulk-copy staged tile kernels when a capacity class holds every tile, else the gather
-  // kernels; experiment knobs MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma).  The alternative limiter
-  // lives in the gather kernels only (the staged kernel's limiter algebra is Venkatakrishnan's).
+  // kernels; experiment knobs MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma).
   const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
   const int tile_class = S->strict ? -1 : ma_fast::pick_tile_class(L.max_tile_cells_real, L.max_tile_faces, L.max_tile_halo);
   const int grad_variant =
-      (tile_class >= 0 && !(gv && !strcmp(gv, "gather")) && cfg.limiter == MA_LIMITER_VENKAT) ? 1 : 0;
+      (tile_class >= 0 && !(gv && !strcmp(gv, "gather"))) ? 1 : 0;
   const int flux_variant = (tile_class < 0 || (fv && !strcmp(fv, "gather"))) ? 0 : 1;
   // the global face -> cell lists are read by the gather kernels only (the staged kernels use the 16-bit tile-local
   // connectivity): 29 bytes per cell that the default FAST configuration does not spend

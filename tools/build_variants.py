@@ -25,6 +25,10 @@ VARIANTS = {
     "t160b3": ["-DMA_C128_FT=160"] + OLD,
     "t192b3": ["-DMA_C128_FT=192"] + OLD,
     "t160b4": ["-DMA_C128_FT=160", "-DMA_C128_FB=4"],
+    "t192b3n": ["-DMA_C128_FT=192", "-DMA_C128_FB=3"],       # RK operands direct (unlike t192b3)
+    "t192b4": ["-DMA_C128_FT=192", "-DMA_C128_FB=4"],
+    "t256b3": ["-DMA_C128_FT=256", "-DMA_C128_FB=3"],
+    "t256b4": ["-DMA_C128_FT=256", "-DMA_C128_FB=4"],
     "t128b4p": ["-DMA_FLUX_PREFETCH_AHEAD=592"],
     "p296": ["-DMA_FLUX_PREFETCH_AHEAD=296", "-DMA_HEADER_AHEAD=1024"],
     "p592h": ["-DMA_FLUX_PREFETCH_AHEAD=592", "-DMA_HEADER_AHEAD=1536"],
