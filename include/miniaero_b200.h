@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MA_ABI_VERSION 2
+#define MA_ABI_VERSION 3
 #define MA_MAX_BC_SETS 16
 
 typedef enum ma_status {
@@ -153,6 +153,11 @@ typedef struct ma_solver_config {
   int overlap_halo; /* non-zero: run interior tiles while the halo exchange is in flight */
   void *stream;     /* cudaStream_t to run on; NULL = a stream owned by the solver */
   int limiter;      /* ma_limiter (second-order runs) */
+  int share_cut_faces; /* FAST staged flux kernel: 0 = library default (on for meshes of at least a few thousand tiles),
+                          1 = every face between two tiles is evaluated by ONE of them (the tile of the earlier of two
+                          flux launches per stage — the checkerboard colours of the tile lattice) and its flux handed to
+                          the other through an exchange buffer, -1 = both tiles evaluate it (one flux launch per stage).
+                          Same results bit for bit either way. */
 } ma_solver_config;
 void ma_solver_config_default(ma_solver_config *cfg);
 

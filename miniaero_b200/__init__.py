@@ -171,7 +171,7 @@ class TimeSolverExplicitRK4:
     is in the caller's cell order."""
 
     def __init__(self, input_mesh_data, options, device=0, arith=ARITH_FAST, tile_dims=(0, 0, 0), block_threads=0,
-                 comm=None, overlap_halo=True, stream=None, limiter=0):
+                 comm=None, overlap_halo=True, stream=None, limiter=0, share_cut_faces=0):
         self._lib = _abi.load()
         self.options = options
         cmesh, self._mesh_keepalive = _as_c_mesh(input_mesh_data)
@@ -186,6 +186,7 @@ class TimeSolverExplicitRK4:
         cfg.overlap_halo = 1 if overlap_halo else 0
         cfg.stream = stream
         cfg.limiter = limiter
+        cfg.share_cut_faces = share_cut_faces
         self._comm = comm
         h = C.c_void_p()
         _abi.check(self._lib.ma_solver_create(C.byref(cmesh), C.byref(options), C.byref(cfg), C.byref(h)))
@@ -193,7 +194,7 @@ class TimeSolverExplicitRK4:
 
     @classmethod
     def from_options(cls, options, rank=0, nranks=1, device=0, arith=ARITH_FAST, tile_dims=(0, 0, 0), block_threads=0,
-                     comm=None, overlap_halo=True, stream=None, limiter=0):
+                     comm=None, overlap_halo=True, stream=None, limiter=0, share_cut_faces=0):
         """Parallel3DMesh + fillMeshData + the constructor in one call (ma_solver_create_structured): the block's
         device layout is built straight from (i, j, k) and its geometry is evaluated on the GPU; the same solver,
         bit for bit, as TimeSolverExplicitRK4(Parallel3DMesh.from_options(options, rank, nranks).fillMeshData(), ...).
@@ -211,6 +212,7 @@ class TimeSolverExplicitRK4:
         cfg.overlap_halo = 1 if overlap_halo else 0
         cfg.stream = stream
         cfg.limiter = limiter
+        cfg.share_cut_faces = share_cut_faces
         self._comm = comm
         h = C.c_void_p()
         _abi.check(self._lib.ma_solver_create_structured(C.byref(options), rank, nranks, C.byref(cfg), C.byref(h)))

@@ -46,7 +46,8 @@ class Mesh(C.Structure):
 
 class SolverConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("arith", C.c_int), ("tile_dims", C.c_int * 3), ("block_threads", C.c_int),
-                ("comm", C.c_void_p), ("overlap_halo", C.c_int), ("stream", C.c_void_p), ("limiter", C.c_int)]
+                ("comm", C.c_void_p), ("overlap_halo", C.c_int), ("stream", C.c_void_p), ("limiter", C.c_int),
+                ("share_cut_faces", C.c_int)]
 
 
 class Timing(C.Structure):

@@ -42,6 +42,19 @@ MA_DEV void cp_async8(double *smem_dst, const double *gmem_src) {
 }
 MA_DEV void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
+// Shared cut faces order a tile group as [first flux pass | second pass] — the two colours of the tile lattice's
+// checkerboard, each in Morton order — so the i-th tile of either pass is one half of the i-th Morton pair.  The
+// gradient sweep has no passes: it walks the group pair by pair (first[0], second[0], first[1], second[1], ...), i.e.
+// in (nearly) the Morton order of the whole group, and the neighbour cells it gathers are again the ones the tiles
+// just before it staged.  n_first == ntiles (or 0): plain order.
+MA_DEV int interleaved_tile(int b, int n_first, int ntiles) {
+  const int n_second = ntiles - n_first;
+  const int paired = n_first < n_second ? n_first : n_second;
+  if (b < 2 * paired) return (b & 1) ? n_first + (b >> 1) : (b >> 1);
+  const int rem = b - 2 * paired;
+  return n_first > n_second ? paired + rem : n_first + paired + rem;
+}
+
 MA_DEV void load_state(const double *__restrict__ base, int stride, int c, double (&v)[5]) {
 #pragma unroll
   for (int k = 0; k < 5; ++k) v[k] = __ldg(base + (size_t)k * stride + c);
@@ -97,8 +110,8 @@ MA_DEV void face_roe_flux(const double (&Vl)[5], const double (&Vr)[5], const Fa
 template <bool SECOND>
 __global__ void __launch_bounds__(MA_GRAD_THREADS, MA_GRAD_MINB) grad_limiter_kernel(const DevMesh m, const double *__restrict__ V_,
                                                            double *__restrict__ grad, double *__restrict__ lim,
-                                                           int tile_begin) {
-  const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
+                                                           int tile_begin, int n_first) {
+  const TileInfoDev T = m.tiles[tile_begin + interleaved_tile(blockIdx.x, n_first, gridDim.x)];
   const TileGeom tg = tile_geom(m, T);
   for (int lc = threadIdx.x; lc < T.cell_count; lc += blockDim.x) {
     const int c = T.cell_start + lc;
@@ -694,7 +707,7 @@ MA_DEV void grad_limiter_cell(const double *__restrict__ sG, const int gstride, 
 template <bool SECOND, class CAP, bool PERSIST, bool GDIRECT = false, bool VANALBADA = false>
 __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP::GRAD_MINB : CAP::GRAD_MINB1)
     grad_limiter_tma_kernel(const DevMesh m, const double *__restrict__ V_, double *__restrict__ grad,
-                            double *__restrict__ lim, int tile_begin, int ntiles) {
+                            double *__restrict__ lim, int tile_begin, int ntiles, int n_first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NG = GDIRECT ? 0 : (SECOND ? 6 : 3);  // staged geometry components: normal (+ centroid)
   constexpr int NGC = SECOND ? 6 : 3;                 // geometry components the arithmetic reads
@@ -715,13 +728,15 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
   }
   int ids0[HPT], ids1[HPT];
   // tile descriptors: current, next, the one after
-  TileInfoDev T0 = tiles[t], T1 = T0, T2 = T0;
-  if (t + G < ntiles) T1 = tiles[t + G];
-  if (t + 2 * G < ntiles) T2 = tiles[t + 2 * G];
+  // (the CTA's tile number t walks the group pair by pair, see interleaved_tile)
+  auto tix = [&](int tile) { return interleaved_tile(tile, n_first, ntiles); };
+  TileInfoDev T0 = tiles[tix(t)], T1 = T0, T2 = T0;
+  if (t + G < ntiles) T1 = tiles[tix(t + G)];
+  if (t + 2 * G < ntiles) T2 = tiles[tix(t + 2 * G)];
   // outside cells of this thread's cut faces of the CTA's tile number `tile` (-1: none); the address needs only
   // the tile index, so the loads fly together with the tile descriptor's
   auto load_ids = [&](int tile, int (&ids)[HPT]) {
-    const int *p = m.tile_halo + (size_t)(tile_begin + tile) * m.halo_stride;
+    const int *p = m.tile_halo + (size_t)(tile_begin + tix(tile)) * m.halo_stride;
 #pragma unroll
     for (int j = 0; j < HPT; ++j) {
       const int h = tid + j * CAP::GRAD_THREADS;
@@ -789,7 +804,7 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
       issue(T1, st ^ 1, ids1);
       load_cell(T1, nxt);
       if (has2) load_ids(t + 2 * G, ids1);                 // consumed at the top of the next iteration
-      if (t + 3 * G < ntiles) T3 = tiles[t + 3 * G];       // consumed two iterations from now
+      if (t + 3 * G < ntiles) T3 = tiles[tix(t + 3 * G)];  // consumed two iterations from now
     }
     mbar_wait(bar0 + 8 * st, (unsigned)(i >> 1) & 1u);
     if (tid < T0.cell_count) {
@@ -934,13 +949,17 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   // together with the tile descriptor's
   const int *halo_ids = m.tile_halo + (size_t)(tile_begin + blockIdx.x) * m.halo_stride;
   const int my_outside = tid < m.halo_stride ? __ldg(halo_ids + tid) : -1;
+  // shared cut faces: where this thread's cut face publishes its flux for the tile on the other side (-1: nowhere)
+  const int *pub_ids = m.tile_pub ? m.tile_pub + (size_t)(tile_begin + blockIdx.x) * m.halo_stride : nullptr;
+  const int my_pub = (pub_ids && tid < m.halo_stride) ? __ldg(pub_ids + tid) : -1;
   const TileInfoDev T = m.tiles[tile_begin + blockIdx.x];
   prefetch_tile_header(m, tile_begin + blockIdx.x, tile_begin + gridDim.x, tid);
-  const int nc = T.cell_count, nf = T.face_count;
+  // faces [0, nf) are evaluated here (closed / boundary, then nh cut faces); [nf, T.face_count) arrive as fluxes
+  const int nc = T.cell_count, nf = T.n_eval, nimp = T.face_count - T.n_eval;
   const int shift = T.cell_start & 1;
   const int hb = (shift + nc + 1) & ~1;  // doubles per staged own-cell run; positions >= hb are outside cells
   const int nh = nf - T.cut_start;
-  const unsigned fcp = (unsigned)(nf + 15) & ~15u;
+  const unsigned fcp = (unsigned)(T.face_count + 15) & ~15u;
   const int sshift = T.cell_start & 7;
   // outside cell of this thread's second cut face (tiles with more cut faces than the CTA has threads)
   // (staged in shared memory when XC > 0; otherwise only its lines are pulled into L2 now and the record is gathered
@@ -961,10 +980,12 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     const int hbb = (sh + TT.cell_count + 1) & ~1;
     const unsigned fcq = (unsigned)(TT.face_count + 15) & ~15u;
     const int ssh = TT.cell_start & 7;
-    const unsigned vbytes = (unsigned)hbb * 8u, gbytes = fcq * 8u, lbytes = fcq * 4u;
+    // geometry of the evaluated faces only: with imports n_eval is even (layout.h), the imported flux columns start there
+    const unsigned vbytes = (unsigned)hbb * 8u, gbytes = (TT.imp_area >= 0 ? (unsigned)TT.n_eval : fcq) * 8u, lbytes = fcq * 4u;
     const unsigned sbytes = (unsigned)((ssh + TT.cell_count + 7) & ~7) * 2u;
+    const unsigned ibytes = (unsigned)((TT.face_count - TT.n_eval + 1) & ~1) * 8u;
     const size_t c0 = (size_t)(TT.cell_start - sh);
-    constexpr int NCOPY = NREC + 11 + NGEOM + 1 + 6;
+    constexpr int NCOPY = NREC + 11 + NGEOM + 1 + 6 + 5;
     for (int i = tid; i < NCOPY; i += 32) {
       if (i < NREC) {
         const double *base = i < R_G   ? a.V + (size_t)i * m.stride
@@ -981,17 +1002,22 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
         emit(smem_addr(sG + gi * FC), m.face_geom + (size_t)6 * TT.face_start + (size_t)gi * fcq, gbytes, true);
       } else if (i == NREC + 11 + NGEOM) {
         emit(smem_addr(sLR), m.face_lr + TT.face_start, lbytes, true);
-      } else {
+      } else if (i < NREC + 11 + NGEOM + 1 + 6) {
         const int s = i - (NREC + 11 + NGEOM + 1);
         emit(smem_addr(sSlot + s * SC), m.slot_face + (size_t)s * m.slot_stride + (TT.cell_start - ssh), sbytes, true);
+      } else if (TT.imp_area >= 0) {  // fluxes of the imported cut faces, published by the tiles of the earlier launch
+        const int k = i - (NREC + 11 + NGEOM + 1 + 6);
+        emit(smem_addr(sG + k * FC + TT.n_eval), m.cut_flux + ((size_t)TT.imp_area * 5 + k) * m.import_capacity, ibytes, true);
       }
     }
   };
   if (tid < 32) {
-    const unsigned vbytes = (unsigned)hb * 8u, gbytes = fcp * 8u, lbytes = fcp * 4u;
+    const unsigned vbytes = (unsigned)hb * 8u, gbytes = (T.imp_area >= 0 ? (unsigned)nf : fcp) * 8u, lbytes = fcp * 4u;
     const unsigned sbytes = (unsigned)((sshift + nc + 7) & ~7) * 2u;
+    const unsigned ibytes = T.imp_area >= 0 ? (unsigned)((nimp + 1) & ~1) * 8u : 0u;
     const int nrk = 1 + (a.kind != 2 ? 5 : 0) + (a.kind != 0 ? 5 : 0);
-    if (tid == 0) mbar_arrive_expect_tx(bar, (NREC + (RKS ? nrk : 0)) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes);
+    if (tid == 0)
+      mbar_arrive_expect_tx(bar, (NREC + (RKS ? nrk : 0)) * vbytes + NGEOM * gbytes + lbytes + 6 * sbytes + 5 * ibytes);
     __syncwarp();
     for_each_run(T, [&](unsigned dst, const void *src, unsigned bytes, bool staged) {
       if (staged)
@@ -1035,7 +1061,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     }
     mbar_cp_async_arrive(bar);
   }
-  if (my_outside >= 0) gather_outside(my_outside);
+  if (my_outside >= 0 && tid < nh) gather_outside(my_outside);  // (imported cut faces have an outside cell too: not needed here)
   if (XC == 0 && CUT2 > 0 && my_outside2 >= 0) {
     const int c = my_outside2;
 #pragma unroll
@@ -1067,7 +1093,7 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
   // ---- phase 1: one flux per tile face.  Work item w: cut face cut_start + w for w < nh, closed / boundary face
   // w - nh otherwise; thread t takes w = t, t + blockDim, ...
   // a cut face: `outside` is the record of the cell on the other side of the tile boundary
-  auto cut_face = [&](int e, auto outside) {
+  auto cut_face = [&](int e, auto outside, int pub) {
     const unsigned lr = sLR[e];
     const int pl = (int)(lr & 0xffffu), pr = (int)(lr >> 16);
     FaceGeom G;
@@ -1089,18 +1115,23 @@ __global__ void __launch_bounds__(CAP::FLUX_THREADS, CAP::FLUX_MINB)
     interior_flux<VISCOUS>(Vl, Vr, gs, G, flux);
 #pragma unroll
     for (int k = 0; k < 5; ++k) sG[k * FC + e] = flux[k];  // this thread's own column: geometry is dead
+    if (pub >= 0) {  // shared cut faces: the tile on the other side runs in the next launch and imports this flux
+#pragma unroll
+      for (int k = 0; k < 5; ++k) m.cut_flux[(size_t)pub + (size_t)k * m.import_capacity] = flux[k];
+    }
   };
   int w = tid;
   if (w < nh) {  // first cut face of this thread: outside record in registers
-    cut_face(T.cut_start + w, RRec{orec});
+    cut_face(T.cut_start + w, RRec{orec}, my_pub);
     w += blockDim.x;
   }
   for (; w < nh; w += blockDim.x) {  // further cut faces: outside record staged in shared memory, else gathered now
+    const int pub = pub_ids ? __ldg(pub_ids + w) : -1;
     if (XC > 0 && blockDim.x == CAP::FLUX_THREADS && w - (int)blockDim.x < XC) {
-      cut_face(T.cut_start + w, XRec{sOut + (w - (int)blockDim.x)});
+      cut_face(T.cut_start + w, XRec{sOut + (w - (int)blockDim.x)}, pub);
     } else {
       gather_outside(w == tid + CAP::FLUX_THREADS && my_outside2 >= 0 ? my_outside2 : __ldg(halo_ids + w));
-      cut_face(T.cut_start + w, RRec{orec});
+      cut_face(T.cut_start + w, RRec{orec}, pub);
     }
   }
   for (; w < nf; w += blockDim.x) {  // closed and boundary faces
@@ -1397,29 +1428,29 @@ size_t flux_smem_bytes(const DevMesh &m, bool second, bool viscous) {
 }
 template <class CAP>
 static cudaError_t launch_grad_tma(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
-                                   int tile_begin, int ntiles, cudaStream_t st) {
+                                   int tile_begin, int ntiles, int n_first, cudaStream_t st) {
   const size_t smem = grad_tma_smem<CAP>(second);
   if (second && m.limiter == 1) {  // the alternative limiter: one tile per CTA (the persistent forms are experiments)
-    grad_limiter_tma_kernel<true, CAP, false, false, true><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+    grad_limiter_tma_kernel<true, CAP, false, false, true><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
     return cudaGetLastError();
   }
   if (grad_persistent() == 2) {
     const int grid = std::min(ntiles, persistent_ctas(CAP::GRAD_MINB1));
     if (second)
-      grad_limiter_tma_kernel<true, CAP, true, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+      grad_limiter_tma_kernel<true, CAP, true, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
     else
-      grad_limiter_tma_kernel<false, CAP, true, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+      grad_limiter_tma_kernel<false, CAP, true, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
   } else if (grad_persistent()) {
     const int grid = std::min(ntiles, persistent_ctas(CAP::GRAD_MINB));
     if (second)
-      grad_limiter_tma_kernel<true, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+      grad_limiter_tma_kernel<true, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
     else
-      grad_limiter_tma_kernel<false, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+      grad_limiter_tma_kernel<false, CAP, true><<<grid, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
   } else {
     if (second)
-      grad_limiter_tma_kernel<true, CAP, false><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+      grad_limiter_tma_kernel<true, CAP, false><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
     else
-      grad_limiter_tma_kernel<false, CAP, false><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles);
+      grad_limiter_tma_kernel<false, CAP, false><<<ntiles, CAP::GRAD_THREADS, smem, st>>>(m, V, grad, lim, tile_begin, ntiles, n_first);
   }
   return cudaGetLastError();
 }
@@ -1468,21 +1499,21 @@ static cudaError_t prepare_tma() {
 #endif
 
 cudaError_t launch_grad_limiter(const DevMesh &m, const double *V, double *grad, double *lim, bool second,
-                                int tile_begin, int ntiles, int threads, cudaStream_t st) {
+                                int tile_begin, int ntiles, int n_first, int threads, cudaStream_t st) {
   if (ntiles <= 0) return cudaSuccess;
 #ifndef MA_STRICT
   if (m.grad_variant == 1) {
     switch (m.tile_class) {
-      case 0: return launch_grad_tma<Cap64>(m, V, grad, lim, second, tile_begin, ntiles, st);
-      case 1: return launch_grad_tma<Cap128>(m, V, grad, lim, second, tile_begin, ntiles, st);
-      case 2: return launch_grad_tma<Cap256>(m, V, grad, lim, second, tile_begin, ntiles, st);
+      case 0: return launch_grad_tma<Cap64>(m, V, grad, lim, second, tile_begin, ntiles, n_first, st);
+      case 1: return launch_grad_tma<Cap128>(m, V, grad, lim, second, tile_begin, ntiles, n_first, st);
+      case 2: return launch_grad_tma<Cap256>(m, V, grad, lim, second, tile_begin, ntiles, n_first, st);
     }
   }
 #endif
   if (second)
-    grad_limiter_kernel<true><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
+    grad_limiter_kernel<true><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin, n_first);
   else
-    grad_limiter_kernel<false><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin);
+    grad_limiter_kernel<false><<<ntiles, threads, 0, st>>>(m, V, grad, lim, tile_begin, n_first);
   return cudaGetLastError();
 }
 

@@ -9,7 +9,10 @@ namespace ma {
 
 struct TileInfoDev {
   int cell_start, cell_count, face_start, face_count;
-  int cut_start, halo_start;  // see ma::TileInfo (layout.h)
+  int cut_start;  // faces [0, cut_start) are closed or boundary faces, [cut_start, face_count) cut faces
+  int n_eval;     // faces [0, n_eval) are evaluated by this tile's CTA; [n_eval, face_count) are imported (layout.h)
+  int imp_area;   // the tile's import area in DevMesh::cut_flux, -1: none
+  int pad_;
 };
 
 // Device mesh in the tile-packed structure-of-arrays layout (see DESIGN.md "Data layout in HBM").
@@ -34,6 +37,12 @@ struct DevMesh {
   const int *face_left, *face_right;   // [n_tile_faces] renumbered cell ids (STRICT kernels only)
   const uint32_t *face_lr;             // [n_tile_faces] tile-local left | right << 16 (boundary: 0xFFFF - type)
   const int *tile_halo;                // outside cell of every cut face, halo_stride entries per tile
+  // shared cut faces (layout.h): where each evaluated cut face publishes its flux (parallel to tile_halo, -1: nowhere),
+  // the exchange buffer [areas][5][import_capacity], and its component stride; null / 0 when every tile evaluates all
+  // of its faces
+  const int *tile_pub;
+  double *cut_flux;
+  int import_capacity;
   double inflow[5];                    // TimeSolverExplicitRK4.h:218-223
 };
 
@@ -53,8 +62,9 @@ struct StageArgs {
 #define MA_DECLARE_KERNEL_API(NS)                                                                                    \
   namespace NS {                                                                                                     \
   /* GreenGauss.h:51-270 + StencilLimiter.h:56-500 fused, cell-centric, tiles [tile_begin, tile_begin+ntiles) */     \
+  /* n_first: tiles of the range that belong to the first flux pass (shared cut faces; == ntiles otherwise) */       \
   cudaError_t launch_grad_limiter(const ma::DevMesh &m, const double *V, double *grad, double *lim, bool second,     \
-                                  int tile_begin, int ntiles, int threads, cudaStream_t st);                         \
+                                  int tile_begin, int ntiles, int n_first, int threads, cudaStream_t st);            \
   /* Flux.h:52-229 + the four *_BC.h + TimeSolverExplicitRK4.h:106-128 fused */                                      \
   cudaError_t launch_flux_rk(const ma::DevMesh &m, const ma::StageArgs &a, bool second, bool viscous,                \
                              int tile_begin, int ntiles, int threads, cudaStream_t st);                              \

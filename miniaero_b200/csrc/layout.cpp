@@ -447,7 +447,8 @@ struct StructuredAccess {
 };
 
 template <class Mesh>
-int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents, bool defer_geometry, HostLayout &L) {
+int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents, bool defer_geometry, bool share_in,
+                      HostLayout &L) {
   const int n_owned = mesh.n_owned, n_ghost = mesh.n_ghost;
   const long n_cells = mesh.n_cells;
   L = HostLayout();
@@ -455,6 +456,8 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   L.n_ghost = n_ghost;
   L.geom_components = with_tangents ? 12 : 6;
   L.geometry_deferred = defer_geometry;
+  const bool share = share_in && !with_tangents;  // the STRICT kernels evaluate every tile face themselves
+  L.share_cut_faces = share;
   L.stride = round_up(n_cells, 32);
   for (int d = 0; d < 3; ++d) L.tile_dims[d] = tile_dims_in[d] > 0 ? tile_dims_in[d] : 8;
   L.max_tile_cells = L.tile_dims[0] * L.tile_dims[1] * L.tile_dims[2];
@@ -568,16 +571,25 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     long first;
     int count;
     int boundary;
+    int colour;  // parity of the tile's position in the tile lattice (shared cut faces: the flux pass it runs in)
   };
   std::vector<RawTile> raw;
   raw.reserve((size_t)n_owned / std::max(1, L.max_tile_cells / 2) + 16);
   for (long i = 0; i < n_owned;) {
     long j = i + 1;
     while (j < n_owned && keys[j].tile == keys[i].tile && (j - i) < L.max_tile_cells) ++j;
-    raw.push_back({i, (int)(j - i), 0});
+    raw.push_back({i, (int)(j - i), 0, 0});
     i = j;
   }
   const long n_tiles = (long)raw.size();
+  if (share) {
+#pragma omp parallel for schedule(static)
+    for (long t = 0; t < n_tiles; ++t) {
+      long q[3];
+      mesh.bin(keys[raw[t].first].cell, q);
+      raw[t].colour = (int)((q[0] / L.tile_dims[0] + q[1] / L.tile_dims[1] + q[2] / L.tile_dims[2]) & 1);
+    }
+  }
   if (n_ghost > 0) {
 #pragma omp parallel for schedule(dynamic, 64)
     for (long t = 0; t < n_tiles; ++t) {
@@ -595,12 +607,18 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   }
   std::vector<long> order;
   order.reserve(n_tiles);
-  for (long t = 0; t < n_tiles; ++t)
-    if (!raw[t].boundary) order.push_back(t);
-  L.n_interior_tiles = (int)order.size();
-  for (long t = 0; t < n_tiles; ++t)
-    if (raw[t].boundary) order.push_back(t);
+  for (int cls = 0; cls < 4; ++cls) {  // launch classes: interior / boundary x first / second pass
+    const size_t before = order.size();
+    for (long t = 0; t < n_tiles; ++t)
+      if ((raw[t].boundary ? 2 : 0) + raw[t].colour == cls) order.push_back(t);
+    L.launch_count[cls] = (int)(order.size() - before);
+  }
+  L.n_interior_tiles = L.launch_count[0] + L.launch_count[1];
   L.n_tiles = (int)n_tiles;
+  // launch class of every tile (in the new order) and, for shared cut faces, the tile of every owned cell
+  std::vector<uint8_t> tile_launch((size_t)n_tiles, 0);
+  std::vector<int> cell_tile;
+  if (share) cell_tile.assign((size_t)n_owned, 0);
   for (long t = 0; t < n_tiles; ++t) L.max_tile_cells_real = std::max(L.max_tile_cells_real, raw[t].count);
   L.tiles.resize(n_tiles);
   L.new2old.resize(n_cells);
@@ -615,11 +633,13 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
 #pragma omp parallel for schedule(dynamic, 64)
     for (long k = 0; k < n_tiles; ++k) {
       const RawTile &r = raw[order[k]];
+      tile_launch[k] = (uint8_t)((r.boundary ? 2 : 0) + r.colour);
       for (int i = 0; i < r.count; ++i) {
         const int oldc = keys[r.first + i].cell;
         const int newc = L.tiles[k].cell_start + i;
         L.new2old[newc] = oldc;
         L.old2new[oldc] = newc;
+        if (share) cell_tile[newc] = (int)k;
       }
     }
     for (long g = n_owned; g < n_cells; ++g) L.new2old[g] = (int)g, L.old2new[g] = (int)g;
@@ -655,14 +675,18 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     if (on < T.cell_start || on >= T.cell_start + T.cell_count) return true;
     return on < newc;
   };
-  // is the cell on the other side of (new cell c, slot s) outside the tile?  (cut face)
-  auto is_cut = [&](const TileInfo &T, int newc, int s) -> bool {
+  // the face (new cell c, slot s) of tile T: 0 = the cell on the other side is in the tile too (or there is none),
+  // 1 = cut face evaluated by this tile, 2 = cut face whose flux this tile imports (shared cut faces: the tile on the
+  // other side runs in an earlier flux launch, evaluates the face and publishes the flux)
+  auto cut_kind = [&](const TileInfo &T, int newc, int s) -> int {
     const int oldc = L.new2old[newc];
     const int oth = mesh.info(oldc, s).other;
-    if (oth < 0) return false;
-    if (oth >= n_owned) return true;
+    if (oth < 0) return 0;
+    if (oth >= n_owned) return 1;
     const int on = L.old2new[oth];
-    return on < T.cell_start || on >= T.cell_start + T.cell_count;
+    if (on >= T.cell_start && on < T.cell_start + T.cell_count) return 0;
+    if (!share) return 1;
+    return tile_launch[cell_tile[on]] < tile_launch[&T - L.tiles.data()] ? 2 : 1;
   };
   const char *fo_env = getenv("MINIAERO_FACE_ORDER");
   const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
@@ -672,24 +696,28 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   // for the staged FAST kernels, that list is re-packed half-warp by half-warp so that the 16 lanes of a shared-memory
   // wavefront read 16 different banks (pack_conflict_free; MINIAERO_FACE_ORDER=slot keeps the plain list).
   // MINIAERO_FACE_ORDER=cell (and STRICT) keeps (cell, slot) order (the gather kernels' L1 locality).
-  struct TileOrder {  // (tile-local cell, slot) of every tile face, in order; group 0 closed / boundary, 1 cut
-    std::vector<uint16_t> lc[2];
-    std::vector<uint8_t> slot[2];
+  struct TileOrder {  // (tile-local cell, slot) of every tile face, in order; group 0 closed / boundary, 1 cut and
+                      // evaluated here, 2 cut and imported
+    std::vector<uint16_t> lc[3];
+    std::vector<uint8_t> slot[3];
+    int dummy_group = -1;  // the LAST entry of this group repeats an evaluated face (pads n_eval to even): it is
+                           // evaluated, but no cell's slot refers to it
   };
   auto compute_order = [&](const TileInfo &T, TileOrder &O) {
     const int shift = T.cell_start & 1;
     struct Emit {
       int c, s;
     };
-    std::vector<Emit> group[2];
-    std::vector<PackItem> pitems[2];
+    std::vector<Emit> group[3];
+    std::vector<PackItem> pitems[3];
     for (int it = 0; it < 6 * T.cell_count; ++it) {
       const int c = T.cell_start + (by_cell ? it / 6 : it % T.cell_count);
       const int s = by_cell ? it % 6 : it / T.cell_count;
       if (!emits(T, c, s)) continue;
-      const bool cut = is_cut(T, c, s);
-      group[cut].push_back({c, s});
-      if (pack) {
+      const int kind = cut_kind(T, c, s);
+      const bool cut = kind != 0;
+      group[kind].push_back({c, s});
+      if (pack && kind < 2) {
         const SlotInfo si = mesh.info(L.new2old[c], s);
         const int side = si.side, own = shift + (c - T.cell_start);
         const int oth = si.other;
@@ -706,8 +734,8 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
       }
     }
     std::vector<int> porder;
-    for (int g = 0; g < 2; ++g) {
-      if (pack) {
+    for (int g = 0; g < 3; ++g) {
+      if (pack && g < 2) {
         // the closed group follows the cut group in the kernel's work-item numbering
         pack_conflict_free(pitems[g], g == 0 ? (int)(group[1].size() & 15) : 0, porder);
       } else {
@@ -721,6 +749,12 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
         O.slot[g][q] = (uint8_t)group[g][porder[q]].s;
       }
     }
+    if (!O.lc[2].empty() && ((O.lc[0].size() + O.lc[1].size()) & 1)) {
+      const int dg = O.lc[0].empty() ? 1 : 0;
+      O.lc[dg].push_back(O.lc[dg][0]);
+      O.slot[dg].push_back(O.slot[dg][0]);
+      O.dummy_group = dg;
+    }
   };
   // structured blocks: tiles with the same key (StructuredAccess::tile_key) share one order
   std::unordered_map<uint64_t, std::shared_ptr<const TileOrder>> order_cache;
@@ -729,6 +763,20 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     uint64_t key = 0;
     if (Mesh::kStructured && L.max_tile_cells < 4096)
       key = mesh.tile_key(L.new2old[T.cell_start], L.tile_dims, T.cell_count, T.cell_start & 1);
+    if (key && share) {
+      // which sides are evaluated here, which imported: part of the pattern (bit 2s: some cut face through slot
+      // direction s is evaluated, bit 2s+1: some is imported; a side that does both is no brick side: no sharing of
+      // the order)
+      unsigned rel = 0;
+      for (int lc = 0; lc < T.cell_count; ++lc)
+        for (int sl = 0; sl < 6; ++sl) {
+          const int kind = cut_kind(T, T.cell_start + lc, sl);
+          if (kind) rel |= 1u << (2 * sl + (kind - 1));
+        }
+      for (int sl = 0; sl < 6; ++sl)
+        if (((rel >> (2 * sl)) & 3u) == 3u) key = 0;
+      if (key) key = key << 12 | rel;
+    }
     if (key) {
       std::lock_guard<std::mutex> lock(order_mutex);
       auto it = order_cache.find(key);
@@ -748,9 +796,11 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
     const std::shared_ptr<const TileOrder> O = order_of(T);
-    const int cut = (int)O->lc[1].size(), cnt = cut + (int)O->lc[0].size();
+    const int cut = (int)(O->lc[1].size() + O->lc[2].size()), cnt = cut + (int)O->lc[0].size();
     L.tiles[k].face_count = cnt;
     L.tiles[k].cut_start = cnt - cut;
+    L.tiles[k].n_eval = cnt - (int)O->lc[2].size();
+    L.tiles[k].imp_area = O->lc[2].empty() ? -1 : 0;  // numbered below
     max_faces = std::max(max_faces, cnt);
     max_local = std::max(max_local, round_up((T.cell_start & 1) + T.cell_count, 2) + cut);
     max_halo = std::max(max_halo, cut);
@@ -775,6 +825,18 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   }
   L.n_tile_faces = fstart[n_tiles];
   L.n_tile_faces_real = real;
+  {
+    int areas = 0, cap = 0;
+    for (long k = 0; k < n_tiles; ++k)
+      if (L.tiles[k].imp_area >= 0) {
+        L.tiles[k].imp_area = areas++;
+        cap = std::max(cap, L.tiles[k].face_count - L.tiles[k].n_eval);
+      }
+    L.n_import_areas = areas;
+    L.import_capacity = round_up(cap, 2);
+    if ((long)areas * 5 * L.import_capacity >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 shared cut-face flux entries");
+    if (share) L.tile_pub.assign((size_t)n_tiles * L.halo_stride, -1);
+  }
   const size_t NF = (size_t)L.n_tile_faces;
   if (defer_geometry)
     L.face_code.assign(NF, 0);
@@ -793,13 +855,14 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     const size_t fcp = (size_t)round_up(T.face_count, 16);
     const int shift = T.cell_start & 1, halo_base = round_up(shift + T.cell_count, 2);
     const std::shared_ptr<const TileOrder> O = order_of(T);
-    for (int g = 0; g < 2; ++g)
+    for (int g = 0; g < 3; ++g)
     for (size_t q = 0; q < O->lc[g].size(); ++q) {
       const int c = T.cell_start + O->lc[g][q], s = O->slot[g][q];
       const int oldc = L.new2old[c];
       {
-        const bool cut = g == 1;
-        const int e = (cut ? T.cut_start : 0) + (int)q;
+        const bool cut = g >= 1;
+        const bool dummy = g == O->dummy_group && q + 1 == O->lc[g].size();  // repeats an evaluated face: no slot owns it
+        const int e = (g == 0 ? 0 : g == 1 ? T.cut_start : T.n_eval) + (int)q;
         const SlotInfo si = mesh.info(oldc, s);
         const int side = si.side;
         const size_t j = (size_t)T.face_start + e;
@@ -836,12 +899,12 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
         }
         const int lc = c - T.cell_start;  // tile-local index of the emitting cell
         if (si.bc_type >= 0) {
-          L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (1 << 14) | (side << 15));
+          if (!dummy) L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (1 << 14) | (side << 15));
           L.face_left[j] = c;
           L.face_right[j] = bc_code(si.bc_type);
           L.face_lr[j] = (uint32_t)(shift + lc) | ((uint32_t)(0xFFFF - si.bc_type) << 16);
         } else {
-          L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
+          if (!dummy) L.slot_face[(size_t)s * L.slot_stride + c] = (uint16_t)(e | (side << 15));
           const int oth_old = si.other;
           const int oth_new = L.old2new[oth_old];
           L.face_left[j] = side == 0 ? c : oth_new;
@@ -853,10 +916,12 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
           } else {
             oth_local = shift + (oth_new - T.cell_start);
             const int os = si.other_slot;
-            L.slot_face[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(e | ((1 - side) << 15));
-            L.slot_nbr[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(shift + lc);
+            if (!dummy) {
+              L.slot_face[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(e | ((1 - side) << 15));
+              L.slot_nbr[(size_t)os * L.slot_stride + oth_new] = (uint16_t)(shift + lc);
+            }
           }
-          L.slot_nbr[(size_t)s * L.slot_stride + c] = (uint16_t)oth_local;
+          if (!dummy) L.slot_nbr[(size_t)s * L.slot_stride + c] = (uint16_t)oth_local;
           L.face_lr[j] = side == 0 ? ((uint32_t)(shift + lc) | ((uint32_t)oth_local << 16))
                                    : ((uint32_t)oth_local | ((uint32_t)(shift + lc) << 16));
         }
@@ -865,6 +930,35 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   }
 
   L.max_frame_error = frame_err;
+
+  if (share) {
+    // where every evaluated cut face publishes its flux: the import slot of the same face in the tile on the other
+    // side, when that tile imports it (slot_face of the other cell is complete now)
+    long bad_pub = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : bad_pub)
+    for (long k = 0; k < n_tiles; ++k) {
+      const TileInfo &T = L.tiles[k];
+      const std::shared_ptr<const TileOrder> O = order_of(T);
+      for (size_t q = 0; q < O->lc[1].size(); ++q) {
+        if (O->dummy_group == 1 && q + 1 == O->lc[1].size()) continue;
+        const int c = T.cell_start + O->lc[1][q], s = O->slot[1][q];
+        const SlotInfo si = mesh.info(L.new2old[c], s);
+        if (si.other < 0 || si.other >= n_owned) continue;
+        const int on = L.old2new[si.other];
+        const long k2 = cell_tile[on];
+        if (!(tile_launch[k] < tile_launch[k2])) continue;  // the other tile evaluates the face itself
+        const TileInfo &T2 = L.tiles[k2];
+        const int e2 = L.slot_face[(size_t)si.other_slot * L.slot_stride + on] & 0x3fff;
+        const int j2 = e2 - T2.n_eval;
+        if (j2 < 0 || e2 >= T2.face_count || T2.imp_area < 0) {
+          ++bad_pub;
+          continue;
+        }
+        L.tile_pub[(size_t)T.halo_start + q] = T2.imp_area * 5 * L.import_capacity + j2;
+      }
+    }
+    if (bad_pub) return ma_set_error(MA_ERR_INVALID, "shared cut faces: a published face is not in the importing tile's list (internal error)");
+  }
 
   lap("tile face lists");
   // ---- 6. halo lists (renumbered), grouped by peer
@@ -898,19 +992,19 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
 
 }  // namespace
 
-int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L) {
+int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L, bool share_cut_faces) {
   ArrayAccess a(mesh);
   int rc = a.prepare();
   if (rc) return rc;
-  return build_layout_impl(a, tile_dims, with_tangents, false, L);
+  return build_layout_impl(a, tile_dims, with_tangents, false, share_cut_faces, L);
 }
 
 int build_layout_structured(const ma_options &opt, int rank, int num_ranks, const int tile_dims[3], bool with_tangents,
-                            bool defer_geometry, HostLayout &L, StructuredGrid *grid) {
+                            bool defer_geometry, HostLayout &L, StructuredGrid *grid, bool share_cut_faces) {
   StructuredAccess a;
   int rc = a.prepare(opt, rank, num_ranks);
   if (rc) return rc;
-  rc = build_layout_impl(a, tile_dims, with_tangents, defer_geometry, L);
+  rc = build_layout_impl(a, tile_dims, with_tangents, defer_geometry, share_cut_faces, L);
   if (rc) return rc;
   if (grid) {
     grid->gen = a.g;

@@ -24,6 +24,14 @@ struct TileInfo {
   int cut_start;   // tile-local index of the first "cut" face (one cell in the tile, the other — owned by a
                    // neighbouring tile or a ghost — outside); faces [0, cut_start) are closed or boundary faces
   int halo_start;  // first entry of the tile in tile_halo; cut face e's outside cell is tile_halo[halo_start + e - cut_start]
+  // Shared cut faces (HostLayout::share_cut_faces): a face between two tiles is evaluated by ONE of them — the one whose
+  // flux launch comes first — which also publishes the flux to the other tile's import area; without sharing every
+  // cut face is evaluated by both tiles.  Faces [0, n_eval) are evaluated by this tile's CTA (closed / boundary faces
+  // [0, cut_start), then the cut faces it evaluates); faces [n_eval, face_count) are cut faces whose flux is imported.
+  // n_eval is even when the tile imports anything (a duplicate of an evaluated face pads an odd count), so that the
+  // imported columns start 16-byte aligned in the staged flux array.
+  int n_eval;
+  int imp_area;    // index of the tile's import area in the cut-flux exchange buffer, -1: none
 };
 
 struct HostLayout {
@@ -77,13 +85,27 @@ struct HostLayout {
   int max_tile_halo = 0;       // largest number of cut faces of a tile
   int halo_stride = 0;         // tile k's outside cells are tile_halo[k * halo_stride ...], padded with -1
 
+  // ---- shared cut faces (FAST staged flux kernel; see TileInfo)
+  bool share_cut_faces = false;
+  // tiles per flux launch, in tile order: [interior first pass, interior second pass, boundary first pass, boundary
+  // second pass] (boundary = touches a ghost cell).  The passes are the two colours of the tile lattice's checkerboard:
+  // face-adjacent bricks never share a launch, and the owner of a cut face is the tile of the earlier launch (tiles of
+  // one launch that do touch — irregular meshes — both evaluate the face, as without sharing).
+  int launch_count[4] = {0, 0, 0, 0};
+  int import_capacity = 0;  // entries per component of an import area (even); component k of import j at 5*cap*area + k*cap + j
+  int n_import_areas = 0;
+  // [n_tiles][halo_stride], parallel to tile_halo: where evaluated cut face cut_start + q publishes its flux (index of
+  // component 0 in the exchange buffer), -1: nowhere (the other side is a ghost, or evaluates the face itself)
+  std::vector<int> tile_pub;
+
   // halo lists in renumbered ids, grouped by neighbour rank ascending
   std::vector<int> send_ids, recv_ids;
   std::vector<int> peer_rank, peer_send_count, peer_recv_count;
 };
 
 // Returns MA_OK or sets the error text.  tile_dims: requested cells per tile per direction.
-int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L);
+int build_layout(const ma_mesh &mesh, const int tile_dims[3], bool with_tangents, HostLayout &L,
+                 bool share_cut_faces = false);
 
 // The same layout for one block of the in-code structured mesh (the reference's Parallel3DMesh / MeshProcessor,
 // Parallel3DMesh.h:173-449) WITHOUT materialising the reference-format arrays: connectivity, numbering and exchange
@@ -94,6 +116,6 @@ struct StructuredGrid {
   GridTables tables;
 };
 int build_layout_structured(const ma_options &opt, int rank, int num_ranks, const int tile_dims[3], bool with_tangents,
-                            bool defer_geometry, HostLayout &L, StructuredGrid *grid);
+                            bool defer_geometry, HostLayout &L, StructuredGrid *grid, bool share_cut_faces = false);
 
 }  // namespace ma

@@ -102,7 +102,9 @@ struct ma_solver {
   uint16_t *d_slot = nullptr, *d_slot_nbr = nullptr;
   int *d_fl = nullptr, *d_fr = nullptr, *d_old2new = nullptr, *d_send_ids = nullptr, *d_recv_ids = nullptr;
   uint32_t *d_face_lr = nullptr;
-  int *d_tile_halo = nullptr;
+  int *d_tile_halo = nullptr, *d_tile_pub = nullptr;
+  double *d_cut_flux = nullptr;
+  int launch_count[4] = {0, 0, 0, 0};  // tiles per flux launch class (layout.h: interior / boundary x first / second pass)
   double *d_Un = nullptr, *d_Acc = nullptr, *d_V[2] = {nullptr, nullptr}, *d_grad = nullptr, *d_lim = nullptr;
   int vcur = 0;  // d_V[vcur] holds the primitives of the state the next stage is evaluated at
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr, *d_stage = nullptr;
@@ -268,6 +270,23 @@ int wait_state_exchange(ma_solver *S) {
   return MA_OK;
 }
 
+// the flux launches of one tile group (0: tiles that touch no ghost cell, 1: the others): one launch, or — shared cut
+// faces — the group's two passes in order (the second imports what the first published; stream order is the only
+// synchronisation)
+int launch_flux_group(ma_solver *S, const Api &K, const ma::StageArgs &a, int group) {
+  int begin = group ? S->launch_count[0] + S->launch_count[1] : 0;
+  if (!S->n_ghost && group) return MA_OK;  // single domain: every tile is in group 0
+  for (int pass = 0; pass < 2; ++pass) {
+    const int n = S->launch_count[2 * group + pass];
+    if (n > 0) {
+      MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, begin, n, S->flux_threads, S->st));
+      S->tm.kernel_launches++;
+    }
+    begin += n;
+  }
+  return MA_OK;
+}
+
 int run_stage(ma_solver *S, const Api &K, int k) {
   static const double alpha[4] = {0.0, 1.0 / 2.0, 1.0 / 2.0, 1.0};                  // TimeSolverExplicitRK4.h:188-191
   static const double beta[4] = {1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0};       // :192-195
@@ -291,11 +310,11 @@ int run_stage(ma_solver *S, const Api &K, int k) {
   if (S->need_grad) {
     {
       ProfScope p(S, &S->tm.grad_seconds);
-      MA_CUDA_TRY(K.grad(S->dm, V, S->d_grad, S->d_lim, S->second, 0, nint, S->grad_threads, S->st));
+      MA_CUDA_TRY(K.grad(S->dm, V, S->d_grad, S->d_lim, S->second, 0, nint, S->launch_count[0], S->grad_threads, S->st));
       S->tm.kernel_launches += nint > 0;
       int rc = wait_state_exchange(S);
       if (rc) return rc;
-      MA_CUDA_TRY(K.grad(S->dm, V, S->d_grad, S->d_lim, S->second, nint, nbnd, S->grad_threads, S->st));
+      MA_CUDA_TRY(K.grad(S->dm, V, S->d_grad, S->d_lim, S->second, nint, nbnd, S->launch_count[2], S->grad_threads, S->st));
       S->tm.kernel_launches += nbnd > 0;
     }
     if (S->n_ghost) {  // gradient (+ limiter) halo: GreenGauss.h:324-338, StencilLimiter.h:618-631
@@ -308,23 +327,23 @@ int run_stage(ma_solver *S, const Api &K, int k) {
     }
     {
       ProfScope p(S, &S->tm.flux_seconds);
-      MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, 0, nint, S->flux_threads, S->st));
-      S->tm.kernel_launches += nint > 0;
+      int rc = launch_flux_group(S, K, a, 0);
+      if (rc) return rc;
       if (S->n_ghost) {
         ProfScope exposed(S, &S->tm.halo_wait_seconds);
         MA_CUDA_TRY(cudaStreamWaitEvent(S->st, S->ev_gl, 0));
       }
-      MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
-      S->tm.kernel_launches += nbnd > 0;
+      rc = launch_flux_group(S, K, a, 1);
+      if (rc) return rc;
     }
   } else {
     ProfScope p(S, &S->tm.flux_seconds);
-    MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, 0, nint, S->flux_threads, S->st));
-    S->tm.kernel_launches += nint > 0;
-    int rc = wait_state_exchange(S);
+    int rc = launch_flux_group(S, K, a, 0);
     if (rc) return rc;
-    MA_CUDA_TRY(K.flux(S->dm, a, S->second, S->viscous, nint, nbnd, S->flux_threads, S->st));
-    S->tm.kernel_launches += nbnd > 0;
+    rc = wait_state_exchange(S);
+    if (rc) return rc;
+    rc = launch_flux_group(S, K, a, 1);
+    if (rc) return rc;
   }
   S->vcur ^= 1;
   return start_state_exchange(S, Vnext);  // ghosts of the next stage state (TimeSolverExplicitRK4.h:359-375)
@@ -477,6 +496,7 @@ void ma_solver_config_default(ma_solver_config *cfg) {
   cfg->overlap_halo = 1;
   cfg->stream = nullptr;
   cfg->limiter = MA_LIMITER_VENKAT;
+  cfg->share_cut_faces = 0;
 }
 
 void ma_solver_destroy(ma_solver *S) {
@@ -485,7 +505,7 @@ void ma_solver_destroy(ma_solver *S) {
   if (S->st) cudaStreamSynchronize(S->st);
   if (S->cs) cudaStreamSynchronize(S->cs);
   void *ptrs[] = {S->d_tiles, S->d_xyz,  S->d_vol,  S->d_geom, S->d_slot,    S->d_fl,      S->d_fr,   S->d_old2new,
-                  S->d_send_ids, S->d_recv_ids, S->d_face_lr, S->d_tile_halo, S->d_slot_nbr, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
+                  S->d_send_ids, S->d_recv_ids, S->d_face_lr, S->d_tile_halo, S->d_tile_pub, S->d_cut_flux, S->d_slot_nbr, S->d_Un, S->d_Acc, S->d_V[0], S->d_V[1], S->d_grad, S->d_lim,
                   S->d_sendbuf, S->d_recvbuf, S->d_stage};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -529,6 +549,18 @@ static int create_prologue(const ma_options *opt, const ma_solver_config *cfg_in
 static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid, const ma_options *opt,
                               const ma_solver_config &cfg, ma_solver **out);
 
+// Shared cut faces (layout.h) pay once a flux launch is many waves of CTAs: two launches per stage instead of one, a
+// sixth fewer face evaluations.  Default: on from `kShareMinCells` owned cells (the reference's own test meshes stay
+// one launch per stage); MINIAERO_SHARE_CUT_FACES=0|1 overrides the default (developer knob), cfg.share_cut_faces both.
+static bool want_shared_cut_faces(const ma_solver_config &cfg, long owned_cells) {
+  const long kShareMinCells = 1L << 20;
+  if (cfg.arith != MA_ARITH_FAST) return false;
+  if (cfg.share_cut_faces > 0) return true;
+  if (cfg.share_cut_faces < 0) return false;
+  if (const char *e = getenv("MINIAERO_SHARE_CUT_FACES")) return e[0] == '1';
+  return owned_cells >= kShareMinCells;
+}
+
 int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver_config *cfg_in, ma_solver **out) {
   if (!mesh || !opt || !out) return ma_set_error(MA_ERR_INVALID, "ma_solver_create: null argument");
   *out = nullptr;
@@ -539,7 +571,7 @@ int ma_solver_create(const ma_mesh *mesh, const ma_options *opt, const ma_solver
   if (mesh->num_ghosts > 0 && !cfg.comm)
     return ma_set_error(MA_ERR_INVALID, "ma_solver_create: mesh has ghost cells but no communicator was given");
   ma::HostLayout L;
-  rc = ma::build_layout(*mesh, td, cfg.arith == MA_ARITH_STRICT, L);
+  rc = ma::build_layout(*mesh, td, cfg.arith == MA_ARITH_STRICT, L, want_shared_cut_faces(cfg, mesh->num_owned_cells));
   if (rc) return rc;
   if (cfg.arith == MA_ARITH_FAST && !(L.max_frame_error <= 1e-9))
     return ma_set_error(MA_ERR_INVALID,
@@ -563,7 +595,10 @@ int ma_solver_create_structured(const ma_options *opt, int rank, int num_ranks, 
   const bool defer = !(hg && hg[0] == '1');
   ma::HostLayout L;
   ma::StructuredGrid grid;
-  rc = ma::build_layout_structured(*opt, rank, num_ranks, td, cfg.arith == MA_ARITH_STRICT, defer, L, &grid);
+  int nproc[3], block[3], nlocal[3] = {0, 0, 0}, offset[3];
+  const bool share = ma_block_decomposition(opt, rank, num_ranks, nproc, block, nlocal, offset) == MA_OK &&
+                     want_shared_cut_faces(cfg, (long)nlocal[0] * nlocal[1] * nlocal[2]);
+  rc = ma::build_layout_structured(*opt, rank, num_ranks, td, cfg.arith == MA_ARITH_STRICT, defer, L, &grid, share);
   if (rc) return rc;
   return solver_from_layout(L, &grid, opt, cfg, out);
 }
@@ -634,7 +669,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
     std::vector<ma::TileInfoDev> tiles(L.tiles.size());
     for (size_t i = 0; i < tiles.size(); ++i)
       tiles[i] = {L.tiles[i].cell_start, L.tiles[i].cell_count, L.tiles[i].face_start, L.tiles[i].face_count,
-                  L.tiles[i].cut_start, L.tiles[i].halo_start};
+                  L.tiles[i].cut_start, L.tiles[i].n_eval, L.tiles[i].imp_area, 0};
     MA_TRY(dev_upload(&S->d_tiles, tiles, &S->device_bytes));
   }
   if (L.geometry_deferred) {
@@ -695,6 +730,11 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   }
   MA_TRY(dev_upload(&S->d_face_lr, L.face_lr, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_tile_halo, L.tile_halo, &S->device_bytes));
+  for (int i = 0; i < 4; ++i) S->launch_count[i] = L.launch_count[i];
+  if (L.share_cut_faces) {
+    MA_TRY(dev_upload(&S->d_tile_pub, L.tile_pub, &S->device_bytes));
+    MA_TRY(dev_alloc(&S->d_cut_flux, (size_t)std::max(1, L.n_import_areas) * 5 * L.import_capacity, &S->device_bytes));
+  }
   MA_TRY(dev_upload(&S->d_old2new, L.old2new, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_send_ids, L.send_ids, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_recv_ids, L.recv_ids, &S->device_bytes));
@@ -736,6 +776,9 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   m.slot_nbr = S->d_slot_nbr;
   m.face_lr = S->d_face_lr;
   m.tile_halo = S->d_tile_halo;
+  m.tile_pub = S->d_tile_pub;
+  m.cut_flux = S->d_cut_flux;
+  m.import_capacity = L.import_capacity;
   m.tiles = S->d_tiles;
   m.cell_xyz = S->d_xyz;
   m.cell_vol = S->d_vol;

@@ -26,7 +26,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from miniaero_b200 import _abi
-    assert lib.ma_abi_version() == 2
+    assert lib.ma_abi_version() == 3
     # plain-C layout checks (no torch / C++ types cross the boundary)
     assert C.sizeof(_abi.Options) == 80
     assert C.sizeof(_abi.Faces) == 56

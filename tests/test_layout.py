@@ -35,6 +35,16 @@ def test_layout_invariants(checker, args):
     _run(checker, args)
 
 
+@pytest.mark.parametrize("args", [(64, 8, 8), (37, 21, 13), (37, 21, 13, 4, 4, 4), (16, 9, 7, 3, 5, 2), (5, 3, 2, 8, 8, 8),
+                                  (128, 4, 4), (9, 9, 9, 16, 2, 2), (64, 32, 32)])
+def test_shared_cut_faces(checker, args):
+    """Shared cut faces (layout.h): every face between two tiles is evaluated by exactly one of them — the one of the
+    earlier flux launch — and published into the other's import slot; a brick tiling needs no face twice."""
+    out = _run(checker, args, {"MINIAERO_CHECK_SHARE": "1"})
+    m = re.search(r"shared cut faces: (\d+) evaluations of (\d+) internal faces \((\d+) evaluated twice\), (\d+) imports", out)
+    assert m and int(m.group(1)) == int(m.group(2)) and int(m.group(3)) == 0
+
+
 @pytest.mark.parametrize("env", [{"MINIAERO_FACE_ORDER": "slot"}, {"MINIAERO_FACE_ORDER": "cell"},
                                  {"MINIAERO_CELL_SWIZZLE": "0"}, {"MINIAERO_TILE_ORDER": "linear"}])
 def test_layout_invariants_under_every_knob(checker, env):

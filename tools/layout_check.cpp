@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "layout.h"
@@ -33,7 +34,8 @@ int main(int argc, char **argv) {
   const ma_mesh *mesh = ma_mesh_view(mh);
   ma::HostLayout L;
   const auto t0 = std::chrono::steady_clock::now();
-  if (ma::build_layout(*mesh, td, false, L)) return printf("layout: %s\n", ma_last_error()), 1;
+  const bool share = getenv("MINIAERO_CHECK_SHARE") != nullptr;  // shared cut faces (layout.h)
+  if (ma::build_layout(*mesh, td, false, L, share)) return printf("layout: %s\n", ma_last_error()), 1;
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("cells %d tiles %d tile faces %ld layout %.2f s\n", L.n_owned, L.n_tiles, L.n_tile_faces_real, sec);
   // ---- invariants
@@ -75,12 +77,64 @@ int main(int argc, char **argv) {
         if (((sf >> 14) & 1) != (L.face_right[j] < 0)) ++bad;
       }
   }
+  // ---- shared cut faces: every face between two owned cells is evaluated exactly once over all tiles (twice only when
+  // the two tiles run in the same flux launch), every imported face has exactly one publisher that targets its slot,
+  // the evaluated count is even wherever something is imported, tiles are ordered by launch class
+  long evals = 0, imports = 0;
+  if (L.share_cut_faces) {
+    std::vector<int> published((size_t)std::max(1, L.n_import_areas) * 5 * L.import_capacity, 0);
+    std::map<std::pair<int, int>, int> count;  // (left, right) cell pair -> evaluations
+    if (L.launch_count[0] + L.launch_count[1] + L.launch_count[2] + L.launch_count[3] != L.n_tiles) ++bad;
+    for (int k = 0; k < L.n_tiles; ++k) {
+      const ma::TileInfo &T = L.tiles[k];
+      const int nimp = T.face_count - T.n_eval;
+      if ((T.imp_area >= 0) != (nimp > 0)) ++bad;
+      if (nimp > 0 && (T.n_eval & 1)) ++bad;
+      if (nimp > L.import_capacity) ++bad;
+      std::vector<char> referenced((size_t)T.face_count, 0);
+      for (int c = T.cell_start; c < T.cell_start + T.cell_count; ++c)
+        for (int s = 0; s < 6; ++s) referenced[L.slot_face[(size_t)s * L.slot_stride + c] & 0x3fff] = 1;
+      int dummies = 0;
+      for (int e = 0; e < T.face_count; ++e) {
+        const size_t j = (size_t)T.face_start + e;
+        if (!referenced[e]) { ++dummies; continue; }   // the padding duplicate of an evaluated face
+        if (L.face_right[j] < 0) continue;
+        if (e < T.n_eval) {
+          ++count[{L.face_left[j], L.face_right[j]}];
+          ++evals;
+        } else {
+          ++imports;
+        }
+        if (e >= T.cut_start && e < T.n_eval) {
+          const int pub = L.tile_pub[(size_t)T.halo_start + (e - T.cut_start)];
+          if (pub >= 0) {
+            if (pub >= (int)published.size()) ++bad; else ++published[pub];
+          }
+        }
+      }
+      if (dummies > 1 || (dummies == 1 && nimp == 0)) ++bad;
+    }
+    for (int k = 0; k < L.n_tiles; ++k) {  // every import slot has exactly one publisher
+      const ma::TileInfo &T = L.tiles[k];
+      for (int j = 0; j < T.face_count - T.n_eval; ++j)
+        if (published[(size_t)T.imp_area * 5 * L.import_capacity + j] != 1) ++bad;
+    }
+    long twice = 0;
+    for (auto &kv : count) {
+      if (kv.second < 1 || kv.second > 2) ++bad;
+      twice += kv.second == 2;
+    }
+    if ((long)count.size() != mesh->internal_faces.nfaces) ++bad;   // single domain: every internal face, no ghosts
+    printf("shared cut faces: %ld evaluations of %d internal faces (%ld evaluated twice), %ld imports, launches %d %d %d %d\n",
+           evals, mesh->internal_faces.nfaces, twice, imports, L.launch_count[0], L.launch_count[1], L.launch_count[2],
+           L.launch_count[3]);
+  }
   printf("invariant violations: %ld\n", bad);
   // ---- wavefront model of the staged flux kernel
   long ideal1 = 0, wf1 = 0, ideal2 = 0, wf2 = 0, paths = 0, warps = 0;
   for (int k = 0; k < L.n_tiles; ++k) {
     const ma::TileInfo &T = L.tiles[k];
-    const int nh = T.face_count - T.cut_start, nf = T.face_count;
+    const int nh = T.n_eval - T.cut_start, nf = T.n_eval;  // the faces this tile's CTA evaluates
     const int shift = T.cell_start & 1, hb = ((shift + T.cell_count + 1) & ~1);
     for (int w0 = 0; w0 < nf; w0 += 16) {  // work items of one half-warp (threads is a multiple of 16)
       int p[4][16];
