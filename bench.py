@@ -514,11 +514,12 @@ def gpu_arm(args):
             traffic_note = "profiles/traffic.json was captured on other kernel sources (hash %s, now %s): not quoted" % (
                 tj.get("source_hash"), source_hash())
     bpcu = BYTES_PER_CELL_UPDATE_O2 if (second or optd["viscous"]) else BYTES_PER_CELL_UPDATE_O1
-    roofline = {"bound": "hbm", "kernel": "flux_rk_tma_kernel (face fluxes + slot-ordered gather + RK stage update)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": "flux_rk_tma_kernel (face fluxes + slot-ordered gather + RK stage update; launched once per pass of the shared-cut-face scheme, the time is the stage's launches together)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": flux_bytes, "launch_ms": flux_ms,
                 "share_of_step": t["flux_seconds"] / t["step_seconds"],
-                "flux_evaluations_per_cell": t["tile_faces_total"] / float(n_owned),
+                "flux_evaluations_per_cell": t["faces_evaluated"] / float(n_owned),
+                "flux_evaluations_per_cell_unshared": t["tile_faces_total"] / float(n_owned),
                 "grad_limiter_kernel": {"launch_ms": grad_ms, "algorithmic_bytes_per_launch": 8.0 * DBL_SWEEP1 * n_owned,
                                         "achieved": (8.0 * DBL_SWEEP1 * n_owned / (grad_ms * 1e-3) / 1e9) if grad_ms > 0 else None,
                                         "frac": (8.0 * DBL_SWEEP1 * n_owned / (grad_ms * 1e-3) / 1e9 / peak) if grad_ms > 0 else None},

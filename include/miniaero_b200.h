@@ -226,6 +226,8 @@ typedef struct ma_timing {
   int num_send_cells, num_recv_cells; /* cells packed / ghosts unpacked per exchange */
   double halo_wait_seconds; /* time the compute stream sat waiting for an exchange before a boundary-tile launch
                                (events; 0 when not profiled): the part of halo_seconds that was NOT hidden */
+  long long faces_evaluated; /* face fluxes evaluated per stage, summed over tiles (== tile_faces_total unless cut
+                                faces are shared: then every face between two tiles counts once) */
 } ma_timing;
 int ma_solver_get_timing(ma_solver *s, ma_timing *t);
 int ma_solver_reset_timing(ma_solver *s);

@@ -55,7 +55,7 @@ class Timing(C.Structure):
                 ("grad_seconds", C.c_double), ("flux_seconds", C.c_double), ("halo_seconds", C.c_double),
                 ("kernel_launches", C.c_longlong), ("device_bytes", C.c_size_t), ("num_tiles", C.c_int),
                 ("tile_faces_total", C.c_int), ("num_interior_tiles", C.c_int), ("num_send_cells", C.c_int),
-                ("num_recv_cells", C.c_int), ("halo_wait_seconds", C.c_double)]
+                ("num_recv_cells", C.c_int), ("halo_wait_seconds", C.c_double), ("faces_evaluated", C.c_longlong)]
 
 
 class Report(C.Structure):

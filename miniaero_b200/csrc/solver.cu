@@ -806,6 +806,11 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   S->tm.device_bytes = S->device_bytes;
   S->tm.num_tiles = S->n_tiles;
   S->tm.tile_faces_total = (int)std::min<long>(L.n_tile_faces_real, 2147483647L);
+  {
+    long long ev = 0;
+    for (const ma::TileInfo &T : L.tiles) ev += T.n_eval;
+    S->tm.faces_evaluated = ev;
+  }
   S->tm.num_interior_tiles = S->n_ghost ? S->n_interior_tiles : S->n_tiles;
   S->tm.num_send_cells = S->n_send;
   S->tm.num_recv_cells = S->n_recv;
