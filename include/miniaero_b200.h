@@ -140,8 +140,8 @@ typedef enum ma_arith {
 typedef enum ma_limiter {
   MA_LIMITER_VENKAT = 0,    /* VenkatLimiter.h:45-73 — what StencilLimiter.h:455,459 call */
   MA_LIMITER_VANALBADA = 1  /* VanAlbadaLimiter.h:45-65 — shipped by the reference (Flux.h:36) but never called; a
-                               maintainer switches by editing those two call sites.  Functional, not tuned: the
-                               gradient/limiter sweep runs through the gather kernels */
+                               maintainer switches by editing those two call sites.  Runs in the same staged
+                               gradient kernel as the default limiter (IEEE divisions per face: not tuned) */
 } ma_limiter;
 
 typedef struct ma_solver_config {

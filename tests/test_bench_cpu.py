@@ -26,6 +26,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "sod_o2_visc"
+    # the arm says which mesh it timed and which workload that is a bounded sample of
+    assert d["config"]["cells"] == d["config"]["mesh"][0] * d["config"]["mesh"][1] * d["config"]["mesh"][2]
+    assert d["config"]["sample_of"]["mesh"] == [512, 512, 256] and d["config"]["sample_of"]["cells_per_gpu"] == 67108864
+    assert d["cpu_baseline"]["one_thread"]["cores"] == 1 and d["cpu_baseline"]["atomics_flux_build"]["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -48,6 +52,17 @@ def test_workloads_are_the_baseline_configs():
     o = bench.workload_options("flatplate_strong", 8)          # configs[4]: fixed 268 M cells
     assert o["nx"] * o["ny"] * o["nz"] == 268435456
     assert bench.BYTES_PER_CELL_UPDATE_O2 == 4648 and bench.BYTES_PER_CELL_UPDATE_O1 == 1928
+    o = bench.workload_options("sod_o1", 1)                    # configs[0]'s physics at the benchmark size
+    assert (o["nx"], o["ny"], o["nz"]) == (512, 512, 256) and o["second_order_space"] == 0 and o["viscous"] == 0
+
+
+def test_traffic_is_quoted_only_for_the_sources_it_was_measured_on():
+    """profiles/traffic.json carries the hash of the kernel sources of its ncu capture; bench.py drops the figure
+    (roofline.traffic = null with a note) when the sources have moved on."""
+    import bench
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        tj = json.load(f)
+    assert len(bench.source_hash()) == 16 and "source_hash" in tj and tj["flux_rk_o2"]["dram_bytes_per_cell"] > 0
 
 
 def test_gpu_arm_fails_loudly_without_a_gpu():
