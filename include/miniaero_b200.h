@@ -234,6 +234,12 @@ int ma_solver_reset_timing(ma_solver *s);
 /* non-zero: bracket every kernel with events to fill grad/flux/halo_seconds (serialises streams) */
 int ma_solver_set_profiling(ma_solver *s, int enabled);
 
+/* Test hook: one of the solver's device-resident layout arrays, copied to `out` (at most `capacity` bytes; the array's
+ * size in bytes is returned through `size` either way).  Names: "tiles", "slot_face", "slot_nbr", "face_lr",
+ * "tile_halo", "tile_pub", "old2new", "face_geom", "cell_xyz", "cell_vol".  tests/test_gpu_topology.py uses it to
+ * check the device-side topology builder against the host builder byte for byte. */
+int ma_solver_debug_array(ma_solver *s, const char *name, void *out, size_t capacity, size_t *size);
+
 /* results.<rank> writer of Solve() (TimeSolverExplicitRK4.h:514-538): x y z rho rhou rhov rhow rhoE,
  * tab separated, `precision` significant digits (the reference uses the ostream default, 6). */
 int ma_write_results(const char *path, const ma_mesh *mesh, const double *solution, int precision);

@@ -295,6 +295,21 @@ class TimeSolverExplicitRK4:
         _abi.check(self._lib.ma_solver_get_field(self._handle, which, out.ctypes.data))
         return out
 
+    def debug_array(self, name, dtype=np.uint8):
+        """Test hook (ma_solver_debug_array): one of the solver's device-resident layout arrays as a numpy array."""
+        size = C.c_size_t(0)
+        _abi.check(self._lib.ma_solver_debug_array(self._handle, name.encode(), None, 0, C.byref(size)))
+        buf = np.zeros(size.value, dtype=np.uint8)
+        if size.value:
+            _abi.check(self._lib.ma_solver_debug_array(self._handle, name.encode(), buf.ctypes.data, size.value, C.byref(size)))
+        return buf.view(dtype) if size.value else buf
+
+    @property
+    def topology_on_device(self):
+        size = C.c_size_t(0)
+        _abi.check(self._lib.ma_solver_debug_array(self._handle, b"topology_on_device", None, 0, C.byref(size)))
+        return size.value == 1
+
     def timing(self):
         t = _abi.Timing()
         _abi.check(self._lib.ma_solver_get_timing(self._handle, C.byref(t)))

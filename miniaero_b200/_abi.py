@@ -76,6 +76,7 @@ if os.environ.get("MINIAERO_B200_LIB"):
 SYMBOLS = {
     "ma_last_error": (C.c_char_p, []),
     "ma_abi_version": (C.c_int, []),
+    "ma_solver_debug_array": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "ma_options_default": (None, [C.POINTER(Options)]),
     "ma_options_read": (C.c_int, [C.c_char_p, C.POINTER(Options)]),
     "ma_mesh_generate": (C.c_int, [C.POINTER(Options), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

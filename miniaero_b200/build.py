@@ -77,7 +77,7 @@ def build(force=False, verbose=False):
         if force or _newer(obj, [src] + headers):
             _run([nvcc] + ARCH + NVCC_COMMON + ["-Xptxas", "-v", "-fmad=false", "-c", src, "-o", obj], log, verbose)
         objs.append(obj)
-        for name in ("solver.cu",):
+        for name in ("solver.cu", "topology_kernels.cu"):
             src = os.path.join(CSRC, name)
             obj = os.path.join(BUILD, name.replace(".cu", ".o"))
             if force or _newer(obj, [src] + headers):

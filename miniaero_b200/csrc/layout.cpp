@@ -446,6 +446,79 @@ struct StructuredAccess {
   int recv_id(long off) const { return recv_ids[off]; }
 };
 
+// The tile-local face order of one tile: (tile-local cell, slot) of every tile face; group 0 closed / boundary, 1 cut and
+// evaluated here, 2 cut and imported (shared cut faces).
+struct TileOrder {
+  std::vector<uint16_t> lc[3];
+  std::vector<uint8_t> slot[3];
+  int dummy_group = -1;  // the LAST entry of this group repeats an evaluated face (pads n_eval to even): it is
+                         // evaluated, but no cell's slot refers to it
+};
+// Inside each group the faces are listed by slot (direction), then by cell — consecutive faces read consecutive own
+// cells and consecutive neighbours — and, for the staged FAST kernels (`pack`), that list is re-packed half-warp by
+// half-warp so that the 16 lanes of a shared-memory wavefront read 16 different banks (pack_conflict_free).  `by_cell`
+// (STRICT, MINIAERO_FACE_ORDER=cell) keeps (cell, slot) order (the gather kernels' L1 locality).
+// The tile is seen through three callbacks over tile-local cell indices, so the same code serves the builder that
+// works on the renumbered global arrays and the one that derives a brick's pattern from (i, j, k) alone:
+//   emits(lc, s)  does cell lc list the face behind its slot s (the in-tile cell with the larger local index does)
+//   kind(lc, s)   0 = closed or boundary face, 1 = cut face evaluated by this tile, 2 = cut face imported
+//   pinfo(lc, s, side, other_local)  which side of the face lc is on (0 = elem1) and, for a closed face, the other
+//                 cell's tile-local index (-1: boundary face)
+template <class Emits, class Kind, class PackInfo>
+void compute_tile_order(int cell_count, int shift, bool by_cell, bool pack, Emits emits, Kind kind_of, PackInfo pinfo,
+                        TileOrder &O) {
+  struct Emit {
+    int lc, s;
+  };
+  std::vector<Emit> group[3];
+  std::vector<PackItem> pitems[3];
+  for (int it = 0; it < 6 * cell_count; ++it) {
+    const int lc = by_cell ? it / 6 : it % cell_count;
+    const int s = by_cell ? it % 6 : it / cell_count;
+    if (!emits(lc, s)) continue;
+    const int kind = kind_of(lc, s);
+    const bool cut = kind != 0;
+    group[kind].push_back({lc, s});
+    if (pack && kind < 2) {
+      int side = 0, other_local = -1;
+      pinfo(lc, s, side, other_local);
+      const int own = shift + lc;
+      PackItem pi;
+      if (cut) {
+        pi = {own, -1, side == 0 ? 2 : 3, 0};
+      } else if (other_local < 0) {
+        pi = {own, -1, 2, 0};
+      } else {
+        const int op = shift + other_local;
+        pi = side == 0 ? PackItem{own, op, 0, 1} : PackItem{op, own, 0, 1};
+      }
+      pitems[cut].push_back(pi);
+    }
+  }
+  std::vector<int> porder;
+  for (int g = 0; g < 3; ++g) {
+    if (pack && g < 2) {
+      // the closed group follows the cut group in the kernel's work-item numbering
+      pack_conflict_free(pitems[g], g == 0 ? (int)(group[1].size() & 15) : 0, porder);
+    } else {
+      porder.resize(group[g].size());
+      for (size_t i = 0; i < group[g].size(); ++i) porder[i] = (int)i;
+    }
+    O.lc[g].resize(group[g].size());
+    O.slot[g].resize(group[g].size());
+    for (size_t q = 0; q < group[g].size(); ++q) {
+      O.lc[g][q] = (uint16_t)group[g][porder[q]].lc;
+      O.slot[g][q] = (uint8_t)group[g][porder[q]].s;
+    }
+  }
+  if (!O.lc[2].empty() && ((O.lc[0].size() + O.lc[1].size()) & 1)) {
+    const int dg = O.lc[0].empty() ? 1 : 0;
+    O.lc[dg].push_back(O.lc[dg][0]);
+    O.slot[dg].push_back(O.slot[dg][0]);
+    O.dummy_group = dg;
+  }
+}
+
 template <class Mesh>
 int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents, bool defer_geometry, bool share_in,
                       HostLayout &L) {
@@ -691,70 +764,18 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   const char *fo_env = getenv("MINIAERO_FACE_ORDER");
   const bool by_cell = with_tangents || (fo_env && !strcmp(fo_env, "cell"));
   const bool pack = !by_cell && !(fo_env && !strcmp(fo_env, "slot"));
-  // The tile-local face order: closed / boundary faces first, cut faces last.  Inside each group the faces are listed
-  // by slot (direction), then by cell — consecutive faces read consecutive own cells and consecutive neighbours — and,
-  // for the staged FAST kernels, that list is re-packed half-warp by half-warp so that the 16 lanes of a shared-memory
-  // wavefront read 16 different banks (pack_conflict_free; MINIAERO_FACE_ORDER=slot keeps the plain list).
-  // MINIAERO_FACE_ORDER=cell (and STRICT) keeps (cell, slot) order (the gather kernels' L1 locality).
-  struct TileOrder {  // (tile-local cell, slot) of every tile face, in order; group 0 closed / boundary, 1 cut and
-                      // evaluated here, 2 cut and imported
-    std::vector<uint16_t> lc[3];
-    std::vector<uint8_t> slot[3];
-    int dummy_group = -1;  // the LAST entry of this group repeats an evaluated face (pads n_eval to even): it is
-                           // evaluated, but no cell's slot refers to it
-  };
+  // The tile-local face order: closed / boundary faces first, cut faces last (compute_tile_order).
   auto compute_order = [&](const TileInfo &T, TileOrder &O) {
-    const int shift = T.cell_start & 1;
-    struct Emit {
-      int c, s;
-    };
-    std::vector<Emit> group[3];
-    std::vector<PackItem> pitems[3];
-    for (int it = 0; it < 6 * T.cell_count; ++it) {
-      const int c = T.cell_start + (by_cell ? it / 6 : it % T.cell_count);
-      const int s = by_cell ? it % 6 : it / T.cell_count;
-      if (!emits(T, c, s)) continue;
-      const int kind = cut_kind(T, c, s);
-      const bool cut = kind != 0;
-      group[kind].push_back({c, s});
-      if (pack && kind < 2) {
-        const SlotInfo si = mesh.info(L.new2old[c], s);
-        const int side = si.side, own = shift + (c - T.cell_start);
-        const int oth = si.other;
-        PackItem pi;
-        if (cut) {
-          pi = {own, -1, side == 0 ? 2 : 3, 0};
-        } else if (oth < 0) {
-          pi = {own, -1, 2, 0};
-        } else {
-          const int op = shift + (L.old2new[oth] - T.cell_start);
-          pi = side == 0 ? PackItem{own, op, 0, 1} : PackItem{op, own, 0, 1};
-        }
-        pitems[cut].push_back(pi);
-      }
-    }
-    std::vector<int> porder;
-    for (int g = 0; g < 3; ++g) {
-      if (pack && g < 2) {
-        // the closed group follows the cut group in the kernel's work-item numbering
-        pack_conflict_free(pitems[g], g == 0 ? (int)(group[1].size() & 15) : 0, porder);
-      } else {
-        porder.resize(group[g].size());
-        for (size_t i = 0; i < group[g].size(); ++i) porder[i] = (int)i;
-      }
-      O.lc[g].resize(group[g].size());
-      O.slot[g].resize(group[g].size());
-      for (size_t q = 0; q < group[g].size(); ++q) {
-        O.lc[g][q] = (uint16_t)(group[g][porder[q]].c - T.cell_start);
-        O.slot[g][q] = (uint8_t)group[g][porder[q]].s;
-      }
-    }
-    if (!O.lc[2].empty() && ((O.lc[0].size() + O.lc[1].size()) & 1)) {
-      const int dg = O.lc[0].empty() ? 1 : 0;
-      O.lc[dg].push_back(O.lc[dg][0]);
-      O.slot[dg].push_back(O.slot[dg][0]);
-      O.dummy_group = dg;
-    }
+    compute_tile_order(
+        T.cell_count, T.cell_start & 1, by_cell, pack, [&](int lc, int sl) { return emits(T, T.cell_start + lc, sl); },
+        [&](int lc, int sl) { return cut_kind(T, T.cell_start + lc, sl); },
+        [&](int lc, int sl, int &side, int &other_local) {
+          const SlotInfo si = mesh.info(L.new2old[T.cell_start + lc], sl);
+          side = si.side;
+          const int on = (si.other >= 0 && si.other < n_owned) ? L.old2new[si.other] : -1;
+          other_local = (on >= T.cell_start && on < T.cell_start + T.cell_count) ? on - T.cell_start : -1;
+        },
+        O);
   };
   // structured blocks: tiles with the same key (StructuredAccess::tile_key) share one order
   std::unordered_map<uint64_t, std::shared_ptr<const TileOrder>> order_cache;
@@ -1009,6 +1030,281 @@ int build_layout_structured(const ma_options &opt, int rank, int num_ranks, cons
   if (grid) {
     grid->gen = a.g;
     grid->tables = std::move(a.tables);
+    grid->gen.xs = grid->tables.xs.data(), grid->gen.ys = grid->tables.ys.data(), grid->gen.zs = grid->tables.zs.data();
+  }
+  return MA_OK;
+}
+
+// ---- topology plan for the device-side builder (layout.h: TopoPlan) -------------------------------------------------
+// Mirrors build_layout_impl<StructuredAccess> step by step — same tile keys, same class order, same local cell order,
+// the same compute_tile_order — but stops at O(tiles) + O(patterns); tests/test_gpu_topology.py compares every array
+// the device then builds with the host builder's, bit for bit.
+int build_topology_plan(const ma_options &opt, int rank, int num_ranks, const int tile_dims_in[3], bool share,
+                        HostLayout &L, StructuredGrid *grid, TopoPlan &P) {
+  StructuredAccess acc;
+  int rc = acc.prepare(opt, rank, num_ranks);
+  if (rc) return rc;
+  const GridGen &g = acc.g;
+  L = HostLayout();
+  P = TopoPlan();
+  const int n_owned = acc.n_owned, n_ghost = acc.n_ghost;
+  const long n_cells = acc.n_cells;
+  L.n_owned = n_owned, L.n_ghost = n_ghost;
+  L.geom_components = 6;
+  L.geometry_deferred = true;
+  L.topology_on_device = true;
+  L.share_cut_faces = share;
+  L.stride = round_up(n_cells, 32);
+  for (int d = 0; d < 3; ++d) L.tile_dims[d] = tile_dims_in[d] > 0 ? tile_dims_in[d] : 8;
+  L.max_tile_cells = L.tile_dims[0] * L.tile_dims[1] * L.tile_dims[2];
+  if (L.max_tile_cells > 4096) return ma_set_error(MA_ERR_INVALID, "tile_dims: at most 4096 cells per tile");
+  if (L.tile_dims[0] > 255 || L.tile_dims[1] > 255 || L.tile_dims[2] > 255)
+    return ma_set_error(MA_ERR_INVALID, "tile_dims: at most 255 cells per direction");
+  for (int f = 0; f < 6; ++f) P.bc_of_face[f] = acc.bc_of_face[f];
+  long nbin[3], ntile_d[3];
+  for (int d = 0; d < 3; ++d) nbin[d] = g.b.n[d], ntile_d[d] = (nbin[d] + L.tile_dims[d] - 1) / L.tile_dims[d];
+  const char *order_env = getenv("MINIAERO_TILE_ORDER");
+  const bool linear_order = order_env && !strcmp(order_env, "linear");
+  const char *sw_env = getenv("MINIAERO_CELL_SWIZZLE");
+  const bool swizzle = L.tile_dims[0] == 4 && L.tile_dims[1] == 4 && L.tile_dims[2] == 8 && !(sw_env && sw_env[0] == '0');
+  const char *fo_env = getenv("MINIAERO_FACE_ORDER");
+  const bool by_cell = fo_env && !strcmp(fo_env, "cell");
+  const bool pack = !by_cell && !(fo_env && !strcmp(fo_env, "slot"));
+  auto local_key_of = [&](long l0, long l1, long l2) -> uint32_t {
+    uint32_t local = (uint32_t)((l0 * L.tile_dims[1] + l1) * L.tile_dims[2] + l2);
+    if (swizzle) {
+      const uint32_t h = local >> 4;
+      local ^= ((h >> 1) & 3u) | ((h & 1u) << 2) | (((h >> 2) & 1u) << 3);
+    }
+    return local;
+  };
+  // ---- tiles in key order, then by launch class
+  struct Ref {
+    uint64_t key;
+    int t[3];
+    int count, boundary, colour;
+  };
+  std::vector<Ref> refs;
+  refs.reserve((size_t)(ntile_d[0] * ntile_d[1] * ntile_d[2]));
+  for (long a = 0; a < ntile_d[0]; ++a)
+    for (long b = 0; b < ntile_d[1]; ++b)
+      for (long c = 0; c < ntile_d[2]; ++c) {
+        Ref r;
+        r.key = linear_order ? ((uint64_t)a * ntile_d[1] + b) * ntile_d[2] + c : morton3(a, b, c);
+        r.t[0] = (int)a, r.t[1] = (int)b, r.t[2] = (int)c;
+        r.count = 1, r.boundary = 0;
+        for (int d = 0; d < 3; ++d) {
+          const long o = (long)r.t[d] * L.tile_dims[d];
+          const long e = std::min<long>(L.tile_dims[d], nbin[d] - o);
+          r.count *= (int)e;
+          if ((o == 0 && g.b.glo[d]) || (o + e == nbin[d] && g.b.ghi[d])) r.boundary = 1;
+        }
+        r.colour = share ? (int)((a + b + c) & 1) : 0;
+        refs.push_back(r);
+      }
+  std::sort(refs.begin(), refs.end(), [](const Ref &x, const Ref &y) { return x.key < y.key; });
+  const long n_tiles = (long)refs.size();
+  std::vector<long> order;
+  order.reserve(n_tiles);
+  for (int cls = 0; cls < 4; ++cls) {
+    const size_t before = order.size();
+    for (long t = 0; t < n_tiles; ++t)
+      if ((refs[t].boundary ? 2 : 0) + refs[t].colour == cls) order.push_back(t);
+    L.launch_count[cls] = (int)(order.size() - before);
+  }
+  L.n_interior_tiles = L.launch_count[0] + L.launch_count[1];
+  L.n_tiles = (int)n_tiles;
+  L.tiles.resize(n_tiles);
+  P.tile_pattern.assign(n_tiles, 0);
+  P.tile_origin.assign((size_t)3 * n_tiles, 0);
+  P.tile_nb.assign((size_t)6 * n_tiles, -1);
+  P.tile_launch.assign(n_tiles, 0);
+  std::vector<int> lattice_tile((size_t)(ntile_d[0] * ntile_d[1] * ntile_d[2]), -1);
+  auto lat = [&](long a, long b, long c) { return (size_t)((a * ntile_d[1] + b) * ntile_d[2] + c); };
+  {
+    long next = 0;
+    for (long k = 0; k < n_tiles; ++k) {
+      const Ref &r = refs[order[k]];
+      L.tiles[k].cell_start = (int)next;
+      L.tiles[k].cell_count = r.count;
+      next += r.count;
+      L.max_tile_cells_real = std::max(L.max_tile_cells_real, r.count);
+      for (int d = 0; d < 3; ++d) P.tile_origin[3 * k + d] = r.t[d] * L.tile_dims[d];
+      P.tile_launch[k] = (uint8_t)((r.boundary ? 2 : 0) + r.colour);
+      lattice_tile[lat(r.t[0], r.t[1], r.t[2])] = (int)k;
+    }
+  }
+  for (long k = 0; k < n_tiles; ++k) {
+    const Ref &r = refs[order[k]];
+    for (int sl = 0; sl < 6; ++sl) {
+      int dd[3];
+      face_dir(sl, dd[0], dd[1], dd[2]);
+      const int d = dd[0] ? 0 : dd[1] ? 1 : 2, dir = dd[d];
+      const long nt = r.t[d] + dir;
+      int nb;
+      if (nt >= 0 && nt < ntile_d[d]) {
+        long q[3] = {r.t[0], r.t[1], r.t[2]};
+        q[d] = nt;
+        nb = lattice_tile[lat(q[0], q[1], q[2])];
+      } else {
+        nb = (dir < 0 ? g.b.glo[d] : g.b.ghi[d]) ? -2 : -1;
+      }
+      P.tile_nb[6 * k + sl] = nb;
+    }
+  }
+  // ---- patterns
+  std::unordered_map<uint64_t, int> pattern_of_key;
+  auto kind_of_side = [&](long k, int sl) -> int {  // of the cut faces through slot direction sl: 0 none, 1 evaluated, 2 imported
+    const int nb = P.tile_nb[6 * k + sl];
+    if (nb == -1) return 0;
+    if (nb == -2) return 1;
+    return (share && P.tile_launch[nb] < P.tile_launch[k]) ? 2 : 1;
+  };
+  for (long k = 0; k < n_tiles; ++k) {
+    const TileInfo &T = L.tiles[k];
+    const int *o = &P.tile_origin[3 * k];
+    int ext[3];
+    for (int d = 0; d < 3; ++d) ext[d] = (int)std::min<long>(L.tile_dims[d], nbin[d] - o[d]);
+    uint64_t key = acc.tile_key((int)g.cell_id(o[0], o[1], o[2]), L.tile_dims, T.cell_count, T.cell_start & 1);
+    unsigned rel = 0;
+    for (int sl = 0; sl < 6; ++sl) {
+      const int kd = kind_of_side(k, sl);
+      if (kd) rel |= 1u << (2 * sl + (kd - 1));
+    }
+    key = key << 12 | rel;
+    auto it = pattern_of_key.find(key);
+    if (it != pattern_of_key.end()) {
+      P.tile_pattern[k] = it->second;
+      continue;
+    }
+    TopoPattern pat;
+    for (int d = 0; d < 3; ++d) pat.ext[d] = ext[d];
+    pat.cell_count = T.cell_count;
+    struct LK {
+      uint32_t local;
+      int cell;
+      uint32_t abc;
+    };
+    std::vector<LK> lk;
+    lk.reserve(T.cell_count);
+    for (int a = 0; a < ext[0]; ++a)
+      for (int b = 0; b < ext[1]; ++b)
+        for (int c = 0; c < ext[2]; ++c)
+          lk.push_back({local_key_of(a, b, c), (int)g.cell_id(o[0] + a, o[1] + b, o[2] + c),
+                        (uint32_t)a | (uint32_t)b << 8 | (uint32_t)c << 16});
+    std::sort(lk.begin(), lk.end(), [](const LK &x, const LK &y) { return x.local != y.local ? x.local < y.local : x.cell < y.cell; });
+    pat.cell_abc.resize(T.cell_count);
+    pat.rank_of.assign((size_t)ext[0] * ext[1] * ext[2], 0);
+    for (int lc = 0; lc < T.cell_count; ++lc) {
+      pat.cell_abc[lc] = lk[lc].abc;
+      const int a = lk[lc].abc & 255, b = (lk[lc].abc >> 8) & 255, c = lk[lc].abc >> 16;
+      pat.rank_of[((size_t)a * ext[1] + b) * ext[2] + c] = (uint16_t)lc;
+    }
+    // the neighbour of (lc, slot): tile-local index when it is in the brick, else -1
+    auto inside = [&](int lc, int sl) -> int {
+      int da, db, dc;
+      face_dir(sl, da, db, dc);
+      const int a = (int)(pat.cell_abc[lc] & 255) + da, b = (int)((pat.cell_abc[lc] >> 8) & 255) + db,
+                c = (int)(pat.cell_abc[lc] >> 16) + dc;
+      if (a < 0 || b < 0 || c < 0 || a >= ext[0] || b >= ext[1] || c >= ext[2]) return -1;
+      return pat.rank_of[((size_t)a * ext[1] + b) * ext[2] + c];
+    };
+    TileOrder O;
+    compute_tile_order(
+        T.cell_count, T.cell_start & 1, by_cell, pack,
+        [&](int lc, int sl) {
+          const int ol = inside(lc, sl);
+          return ol < 0 ? true : ol < lc;
+        },
+        [&](int lc, int sl) { return inside(lc, sl) >= 0 ? 0 : kind_of_side(k, sl); },
+        [&](int lc, int sl, int &side, int &other_local) {
+          const int a = (int)(pat.cell_abc[lc] & 255), b = (int)((pat.cell_abc[lc] >> 8) & 255), c = (int)(pat.cell_abc[lc] >> 16);
+          side = acc.info((int)g.cell_id(o[0] + a, o[1] + b, o[2] + c), sl).side;
+          other_local = inside(lc, sl);
+        },
+        O);
+    pat.cut_start = (int)O.lc[0].size();
+    pat.n_eval = pat.cut_start + (int)O.lc[1].size();
+    pat.face_count = pat.n_eval + (int)O.lc[2].size();
+    pat.dummy_face = O.dummy_group < 0 ? -1 : (O.dummy_group == 0 ? pat.cut_start - 1 : pat.n_eval - 1);
+    for (int gi = 0; gi < 3; ++gi)
+      for (size_t q = 0; q < O.lc[gi].size(); ++q) {
+        pat.face_lc.push_back(O.lc[gi][q]);
+        pat.face_slot.push_back(O.slot[gi][q]);
+      }
+    const int id = (int)P.patterns.size();
+    P.patterns.push_back(std::move(pat));
+    pattern_of_key.emplace(key, id);
+    P.tile_pattern[k] = id;
+  }
+  // ---- descriptors, sizes
+  int max_faces = 0, max_local = 0, max_halo = 0;
+  for (long k = 0; k < n_tiles; ++k) {
+    const TopoPattern &pat = P.patterns[P.tile_pattern[k]];
+    TileInfo &T = L.tiles[k];
+    T.face_count = pat.face_count, T.cut_start = pat.cut_start, T.n_eval = pat.n_eval;
+    T.imp_area = pat.face_count > pat.n_eval ? 0 : -1;
+    const int cut = pat.face_count - pat.cut_start;
+    max_faces = std::max(max_faces, pat.face_count);
+    max_local = std::max(max_local, round_up((T.cell_start & 1) + T.cell_count, 2) + cut);
+    max_halo = std::max(max_halo, cut);
+  }
+  if (max_faces >= 16384) return ma_set_error(MA_ERR_INVALID, "tile has more than 16383 faces; use smaller tile_dims");
+  if (max_local >= 0xFFF0 - 2) return ma_set_error(MA_ERR_INVALID, "tile has too many cells + cut faces; use smaller tile_dims");
+  L.max_tile_faces = max_faces, L.max_tile_local = max_local, L.max_tile_halo = max_halo;
+  L.halo_stride = std::max(4, round_up(max_halo, 4));
+  if ((long)n_tiles * L.halo_stride >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 tile halo entries");
+  {
+    long fstart = 0, real = 0;
+    int areas = 0, cap = 0;
+    for (long k = 0; k < n_tiles; ++k) {
+      TileInfo &T = L.tiles[k];
+      T.face_start = (int)fstart;
+      T.halo_start = (int)(k * L.halo_stride);
+      fstart += round_up(T.face_count, 16);
+      real += T.face_count;
+      if (fstart >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 tile faces");
+      if (T.imp_area >= 0) {
+        T.imp_area = areas++;
+        cap = std::max(cap, T.face_count - T.n_eval);
+      }
+    }
+    L.n_tile_faces = fstart, L.n_tile_faces_real = real;
+    L.n_import_areas = areas;
+    L.import_capacity = round_up(cap, 2);
+    if ((long)areas * 5 * L.import_capacity >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 shared cut-face flux entries");
+  }
+  L.slot_stride = round_up(n_owned, 32);
+  // ---- exchange lists in renumbered ids (the renumbering itself happens on the device)
+  auto old2new = [&](int old) -> int {
+    if (old >= n_owned) return old;
+    int i, j, k2;
+    g.cell_ijk(old, i, j, k2);
+    const long t0 = i / L.tile_dims[0], t1 = j / L.tile_dims[1], t2 = k2 / L.tile_dims[2];
+    const int k = lattice_tile[lat(t0, t1, t2)];
+    const TopoPattern &pat = P.patterns[P.tile_pattern[k]];
+    const int a = i - P.tile_origin[3 * k], b = j - P.tile_origin[3 * k + 1], c = k2 - P.tile_origin[3 * k + 2];
+    return L.tiles[k].cell_start + pat.rank_of[((size_t)a * pat.ext[1] + b) * pat.ext[2] + c];
+  };
+  if (n_ghost > 0) {
+    long so = 0, ro = 0;
+    for (int p = 0; p < acc.num_ranks(); ++p) {
+      const int sc = acc.send_count(p), rcnt = acc.recv_count(p);
+      if (p == acc.my_rank() || (sc == 0 && rcnt == 0)) {
+        so += sc, ro += rcnt;
+        continue;
+      }
+      L.peer_rank.push_back(p);
+      L.peer_send_count.push_back(sc);
+      L.peer_recv_count.push_back(rcnt);
+      for (int i = 0; i < sc; ++i) L.send_ids.push_back(old2new(acc.send_id(so + i)));
+      for (int i = 0; i < rcnt; ++i) L.recv_ids.push_back(old2new(acc.recv_id(ro + i)));
+      so += sc, ro += rcnt;
+    }
+  }
+  if (grid) {
+    grid->gen = acc.g;
+    grid->tables = std::move(acc.tables);
     grid->gen.xs = grid->tables.xs.data(), grid->gen.ys = grid->tables.ys.data(), grid->gen.zs = grid->tables.zs.data();
   }
   return MA_OK;

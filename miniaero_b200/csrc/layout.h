@@ -98,6 +98,10 @@ struct HostLayout {
   // component 0 in the exchange buffer), -1: nowhere (the other side is a ghost, or evaluates the face itself)
   std::vector<int> tile_pub;
 
+  // true: only the O(tiles) members and the exchange lists below are filled; the O(cells) arrays are built on the
+  // device from a TopoPlan (build_topology_plan)
+  bool topology_on_device = false;
+
   // halo lists in renumbered ids, grouped by neighbour rank ascending
   std::vector<int> send_ids, recv_ids;
   std::vector<int> peer_rank, peer_send_count, peer_recv_count;
@@ -117,5 +121,34 @@ struct StructuredGrid {
 };
 int build_layout_structured(const ma_options &opt, int rank, int num_ranks, const int tile_dims[3], bool with_tangents,
                             bool defer_geometry, HostLayout &L, StructuredGrid *grid, bool share_cut_faces = false);
+
+// ---- topology on the device (structured blocks, FAST staged kernels) ------------------------------------------------
+// The O(cells) part of the layout — cell renumbering, slot maps, tile-local connectivity, face codes, outside-cell
+// lists, publish slots — is a pure function of (tile, position in the tile's pattern): tiles of a structured block
+// fall into a few dozen PATTERNS (brick extents x what lies behind each of the six sides x parity of the first cell),
+// and a pattern fixes the tile-local order of cells and faces.  build_topology_plan() does the O(tiles) and
+// O(patterns) work on the host — tile order, descriptors, one TileOrder per pattern (the same compute_tile_order the
+// host builder uses, so the two builders cannot drift apart) — and topology_kernels.cu stamps the patterns on the
+// device.  HostLayout then carries only its O(tiles) members and the (renumbered) exchange lists; the O(cells)
+// vectors stay empty.
+struct TopoPattern {
+  int ext[3];                       // brick extents (cells)
+  int cell_count, face_count, cut_start, n_eval;
+  int dummy_face;                   // face index of the padding duplicate, -1: none
+  std::vector<uint32_t> cell_abc;   // [cell_count] brick-local (a, b, c) of the lc-th cell: a | b << 8 | c << 16
+  std::vector<uint16_t> rank_of;    // [ext0 * ext1 * ext2] (a * ext1 + b) * ext2 + c -> lc
+  std::vector<uint16_t> face_lc;    // [face_count] emitting cell of face e
+  std::vector<uint8_t> face_slot;   // [face_count] its slot
+};
+struct TopoPlan {
+  std::vector<TopoPattern> patterns;
+  std::vector<int> tile_pattern;    // [n_tiles]
+  std::vector<int> tile_origin;     // [n_tiles][3] block-local (i, j, k) of the brick's first cell
+  std::vector<int> tile_nb;         // [n_tiles][6] tile behind slot direction s; -1 domain boundary, -2 ghost layer
+  std::vector<uint8_t> tile_launch; // [n_tiles] flux launch class (layout.h: HostLayout::launch_count)
+  int bc_of_face[6];                // ma_bc_type of the domain side behind local face f
+};
+int build_topology_plan(const ma_options &opt, int rank, int num_ranks, const int tile_dims[3], bool share_cut_faces,
+                        HostLayout &L, StructuredGrid *grid, TopoPlan &plan);
 
 }  // namespace ma

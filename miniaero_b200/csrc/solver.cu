@@ -21,6 +21,7 @@
 #include "kernels.h"
 #include "layout.h"
 #include "miniaero_b200.h"
+#include "topology_kernels.h"
 
 namespace {
 
@@ -105,6 +106,8 @@ struct ma_solver {
   int *d_tile_halo = nullptr, *d_tile_pub = nullptr;
   double *d_cut_flux = nullptr;
   int launch_count[4] = {0, 0, 0, 0};  // tiles per flux launch class (layout.h: interior / boundary x first / second pass)
+  size_t n_slot_entries = 0, n_face_entries = 0, n_halo_entries = 0, n_geom_entries = 0;  // array sizes (debug hook)
+  bool topology_on_device = false;
   double *d_Un = nullptr, *d_Acc = nullptr, *d_V[2] = {nullptr, nullptr}, *d_grad = nullptr, *d_lim = nullptr;
   int vcur = 0;  // d_V[vcur] holds the primitives of the state the next stage is evaluated at
   double *d_sendbuf = nullptr, *d_recvbuf = nullptr, *d_stage = nullptr;
@@ -547,7 +550,7 @@ static int create_prologue(const ma_options *opt, const ma_solver_config *cfg_in
 }
 
 static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid, const ma_options *opt,
-                              const ma_solver_config &cfg, ma_solver **out);
+                              const ma_solver_config &cfg, ma_solver **out, const ma::TopoPlan *plan = nullptr);
 
 // Shared cut faces (layout.h) pay once a flux launch is many waves of CTAs: two launches per stage instead of one, a
 // sixth fewer face evaluations.  Default: on from `kShareMinCells` owned cells (the reference's own test meshes stay
@@ -598,13 +601,111 @@ int ma_solver_create_structured(const ma_options *opt, int rank, int num_ranks, 
   int nproc[3], block[3], nlocal[3] = {0, 0, 0}, offset[3];
   const bool share = ma_block_decomposition(opt, rank, num_ranks, nproc, block, nlocal, offset) == MA_OK &&
                      want_shared_cut_faces(cfg, (long)nlocal[0] * nlocal[1] * nlocal[2]);
+  // Topology on the device (layout.h: TopoPlan; MINIAERO_DEVICE_TOPOLOGY=0 keeps it on the host): the host does the
+  // O(tiles) + O(patterns) part, the device stamps the patterns.  Needs the staged kernels (the gather kernels read
+  // global face -> cell lists the device builder does not make): a block whose tiles fit no capacity class, the STRICT
+  // arithmetic and the gather-kernel knobs go through the host builder.
+  {
+    const char *dt = getenv("MINIAERO_DEVICE_TOPOLOGY"), *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
+    const bool wanted = cfg.arith == MA_ARITH_FAST && defer && !(dt && dt[0] == '0') && !(gv && !strcmp(gv, "gather")) &&
+                        !(fv && !strcmp(fv, "gather"));
+    if (wanted) {
+      ma::TopoPlan plan;
+      rc = ma::build_topology_plan(*opt, rank, num_ranks, td, share, L, &grid, plan);
+      if (rc) return rc;
+      if (ma_fast::pick_tile_class(L.max_tile_cells_real, L.max_tile_faces, L.max_tile_halo) >= 0)
+        return solver_from_layout(L, &grid, opt, cfg, out, &plan);
+    }
+  }
   rc = ma::build_layout_structured(*opt, rank, num_ranks, td, cfg.arith == MA_ARITH_STRICT, defer, L, &grid, share);
   if (rc) return rc;
   return solver_from_layout(L, &grid, opt, cfg, out);
 }
 
+// Topology on the device (layout.h: TopoPlan): allocates the solver's slot maps, tile-local connectivity, outside-cell
+// and publish lists and the caller-order map, uploads the plan's O(tiles) + O(patterns) tables and stamps the patterns
+// (topology_kernels.cu).  d_code / d_new2old are temporaries the geometry kernels need next; the caller frees them.
+static int build_topology_on_device(ma_solver *S, const ma::HostLayout &L, const ma::StructuredGrid &grid,
+                                    const ma::TopoPlan &P, uint32_t **d_code, int **d_new2old) {
+  const long n_cells = (long)L.n_owned + L.n_ghost;
+  std::vector<int> pat_ext, pat_dummy, pat_cell_off, pat_rank_off, pat_face_off;
+  std::vector<uint32_t> cell_abc;
+  std::vector<uint16_t> rank_of, face_lc;
+  std::vector<uint8_t> face_slot;
+  for (const ma::TopoPattern &p : P.patterns) {
+    for (int d = 0; d < 3; ++d) pat_ext.push_back(p.ext[d]);
+    pat_dummy.push_back(p.dummy_face);
+    pat_cell_off.push_back((int)cell_abc.size());
+    pat_rank_off.push_back((int)rank_of.size());
+    pat_face_off.push_back((int)face_lc.size());
+    cell_abc.insert(cell_abc.end(), p.cell_abc.begin(), p.cell_abc.end());
+    rank_of.insert(rank_of.end(), p.rank_of.begin(), p.rank_of.end());
+    face_lc.insert(face_lc.end(), p.face_lc.begin(), p.face_lc.end());
+    face_slot.insert(face_slot.end(), p.face_slot.begin(), p.face_slot.end());
+  }
+  // scratch: the plan's tables
+  int *d_tp = nullptr, *d_to = nullptr, *d_tn = nullptr, *d_pe = nullptr, *d_pd = nullptr, *d_pc = nullptr, *d_pr = nullptr,
+      *d_pf = nullptr;
+  unsigned char *d_tl = nullptr;
+  uint32_t *d_abc = nullptr;
+  uint16_t *d_rank = nullptr, *d_flc = nullptr;
+  uint8_t *d_fs = nullptr;
+  size_t scratch = 0;
+  int rc = dev_upload(&d_tp, P.tile_pattern, &scratch);
+  if (!rc) rc = dev_upload(&d_to, P.tile_origin, &scratch);
+  if (!rc) rc = dev_upload(&d_tn, P.tile_nb, &scratch);
+  if (!rc) rc = dev_upload(&d_tl, P.tile_launch, &scratch);
+  if (!rc) rc = dev_upload(&d_pe, pat_ext, &scratch);
+  if (!rc) rc = dev_upload(&d_pd, pat_dummy, &scratch);
+  if (!rc) rc = dev_upload(&d_pc, pat_cell_off, &scratch);
+  if (!rc) rc = dev_upload(&d_pr, pat_rank_off, &scratch);
+  if (!rc) rc = dev_upload(&d_pf, pat_face_off, &scratch);
+  if (!rc) rc = dev_upload(&d_abc, cell_abc, &scratch);
+  if (!rc) rc = dev_upload(&d_rank, rank_of, &scratch);
+  if (!rc) rc = dev_upload(&d_flc, face_lc, &scratch);
+  if (!rc) rc = dev_upload(&d_fs, face_slot, &scratch);
+  // persistent: what the stage kernels and the get / set calls read
+  const size_t NS = (size_t)6 * L.slot_stride, NF = (size_t)L.n_tile_faces, NH = (size_t)L.n_tiles * L.halo_stride;
+  if (!rc) rc = dev_alloc(&S->d_slot, NS, &S->device_bytes);
+  if (!rc) rc = dev_alloc(&S->d_slot_nbr, NS, &S->device_bytes);
+  if (!rc) rc = dev_alloc(&S->d_face_lr, NF, &S->device_bytes);
+  if (!rc) rc = dev_alloc(&S->d_tile_halo, NH, &S->device_bytes);
+  if (!rc && L.share_cut_faces) rc = dev_alloc(&S->d_tile_pub, NH, &S->device_bytes);
+  if (!rc) rc = dev_alloc(&S->d_old2new, (size_t)n_cells, &S->device_bytes);
+  if (!rc) rc = dev_alloc(d_code, NF, &scratch);
+  if (!rc) rc = dev_alloc(d_new2old, (size_t)n_cells, &scratch);
+  cudaError_t ce = cudaSuccess;
+  if (!rc) {
+    ce = cudaMemsetAsync(S->d_slot, 0, NS * sizeof(uint16_t), S->st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(S->d_slot_nbr, 0xFF, NS * sizeof(uint16_t), S->st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(S->d_face_lr, 0, NF * sizeof(uint32_t), S->st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(*d_code, 0, NF * sizeof(uint32_t), S->st);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(S->d_tile_halo, 0xFF, NH * sizeof(int), S->st);
+    if (ce == cudaSuccess && S->d_tile_pub) ce = cudaMemsetAsync(S->d_tile_pub, 0xFF, NH * sizeof(int), S->st);
+    ma::TopoView t;
+    t.g = grid.gen;
+    t.g.xs = t.g.ys = t.g.zs = nullptr;  // numbering only
+    t.n_owned = L.n_owned, t.n_tiles = L.n_tiles, t.slot_stride = L.slot_stride, t.halo_stride = L.halo_stride;
+    t.import_capacity = L.import_capacity;
+    for (int f = 0; f < 6; ++f) t.bc_of_face[f] = P.bc_of_face[f];
+    t.tiles = S->d_tiles, t.tile_pattern = d_tp, t.tile_origin = d_to, t.tile_nb = d_tn, t.tile_launch = d_tl;
+    t.pat_ext = d_pe, t.pat_dummy = d_pd, t.pat_cell_off = d_pc, t.pat_rank_off = d_pr, t.pat_face_off = d_pf;
+    t.cell_abc = d_abc, t.rank_of = d_rank, t.face_lc = d_flc, t.face_slot = d_fs;
+    t.new2old = *d_new2old, t.old2new = S->d_old2new, t.slot_face = S->d_slot, t.slot_nbr = S->d_slot_nbr;
+    t.face_lr = S->d_face_lr, t.face_code = *d_code, t.tile_halo = S->d_tile_halo, t.tile_pub = S->d_tile_pub;
+    if (ce == cudaSuccess) ce = ma::launch_device_topology(t, n_cells, S->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(S->st);
+  }
+  for (void *p : {(void *)d_tp, (void *)d_to, (void *)d_tn, (void *)d_tl, (void *)d_pe, (void *)d_pd, (void *)d_pc, (void *)d_pr,
+                  (void *)d_pf, (void *)d_abc, (void *)d_rank, (void *)d_flc, (void *)d_fs})
+    if (p) cudaFree(p);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return ma_set_error(MA_ERR_CUDA, std::string("device topology: ") + cudaGetErrorString(ce));
+  return MA_OK;
+}
+
 static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid, const ma_options *opt,
-                              const ma_solver_config &cfg, ma_solver **out) {
+                              const ma_solver_config &cfg, ma_solver **out, const ma::TopoPlan *plan) {
   int rc = MA_OK;
   ma_solver *S = new ma_solver();
   std::memset(&S->tm, 0, sizeof(S->tm));
@@ -686,11 +787,16 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
     uint32_t *d_code = nullptr;
     int *d_new2old = nullptr;
     size_t scratch = 0;
-    int r2 = dev_upload(&d_xs, grid->tables.xs, &scratch);
+    int r2 = MA_OK;
+    if (plan) {  // the topology itself is built on the device: face codes and the cell permutation are already there
+      r2 = build_topology_on_device(S, L, *grid, *plan, &d_code, &d_new2old);
+    } else {
+      r2 = dev_upload(&d_code, L.face_code, &scratch);
+      if (!r2) r2 = dev_upload(&d_new2old, L.new2old, &scratch);
+    }
+    if (!r2) r2 = dev_upload(&d_xs, grid->tables.xs, &scratch);
     if (!r2) r2 = dev_upload(&d_ys, grid->tables.ys, &scratch);
     if (!r2) r2 = dev_upload(&d_zs, grid->tables.zs, &scratch);
-    if (!r2) r2 = dev_upload(&d_code, L.face_code, &scratch);
-    if (!r2) r2 = dev_upload(&d_new2old, L.new2old, &scratch);
     cudaError_t ge = cudaSuccess;
     if (!r2) {
       ma::GridGen g = grid->gen;
@@ -713,8 +819,10 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
     MA_TRY(dev_upload(&S->d_geom, L.face_geom, &S->device_bytes));
     std::vector<double>().swap(L.face_geom);
   }
-  MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
-  if (!S->strict) MA_TRY(dev_upload(&S->d_slot_nbr, L.slot_nbr, &S->device_bytes));
+  if (!plan) {
+    MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));
+    if (!S->strict) MA_TRY(dev_upload(&S->d_slot_nbr, L.slot_nbr, &S->device_bytes));
+  }
   // kernel variants (FAST: the bulk-copy staged tile kernels when a capacity class holds every tile, else the gather
   // kernels; experiment knobs MINIAERO_GRAD_KERNEL / MINIAERO_FLUX_KERNEL = gather | tma).
   const char *gv = getenv("MINIAERO_GRAD_KERNEL"), *fv = getenv("MINIAERO_FLUX_KERNEL");
@@ -724,18 +832,26 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   const int flux_variant = (tile_class < 0 || (fv && !strcmp(fv, "gather"))) ? 0 : 1;
   // the global face -> cell lists are read by the gather kernels only (the staged kernels use the 16-bit tile-local
   // connectivity): 29 bytes per cell that the default FAST configuration does not spend
+  if (plan && (S->strict || grad_variant == 0 || flux_variant == 0)) {
+    ma_solver_destroy(S);
+    return ma_set_error(MA_ERR_INVALID, "device topology without the staged kernels (internal error)");
+  }
   if (S->strict || grad_variant == 0 || flux_variant == 0) {
     MA_TRY(dev_upload(&S->d_fl, L.face_left, &S->device_bytes));
     MA_TRY(dev_upload(&S->d_fr, L.face_right, &S->device_bytes));
   }
-  MA_TRY(dev_upload(&S->d_face_lr, L.face_lr, &S->device_bytes));
-  MA_TRY(dev_upload(&S->d_tile_halo, L.tile_halo, &S->device_bytes));
-  for (int i = 0; i < 4; ++i) S->launch_count[i] = L.launch_count[i];
-  if (L.share_cut_faces) {
-    MA_TRY(dev_upload(&S->d_tile_pub, L.tile_pub, &S->device_bytes));
-    MA_TRY(dev_alloc(&S->d_cut_flux, (size_t)std::max(1, L.n_import_areas) * 5 * L.import_capacity, &S->device_bytes));
+  if (!plan) {
+    MA_TRY(dev_upload(&S->d_face_lr, L.face_lr, &S->device_bytes));
+    MA_TRY(dev_upload(&S->d_tile_halo, L.tile_halo, &S->device_bytes));
+    if (L.share_cut_faces) MA_TRY(dev_upload(&S->d_tile_pub, L.tile_pub, &S->device_bytes));
+    MA_TRY(dev_upload(&S->d_old2new, L.old2new, &S->device_bytes));
   }
-  MA_TRY(dev_upload(&S->d_old2new, L.old2new, &S->device_bytes));
+  for (int i = 0; i < 4; ++i) S->launch_count[i] = L.launch_count[i];
+  S->n_slot_entries = (size_t)6 * L.slot_stride, S->n_face_entries = (size_t)L.n_tile_faces;
+  S->n_halo_entries = (size_t)L.n_tiles * L.halo_stride, S->n_geom_entries = (size_t)L.geom_components * L.n_tile_faces;
+  S->topology_on_device = plan != nullptr;
+  if (L.share_cut_faces)
+    MA_TRY(dev_alloc(&S->d_cut_flux, (size_t)std::max(1, L.n_import_areas) * 5 * L.import_capacity, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_send_ids, L.send_ids, &S->device_bytes));
   MA_TRY(dev_upload(&S->d_recv_ids, L.recv_ids, &S->device_bytes));
   const size_t sv = (size_t)5 * S->stride;
@@ -1000,6 +1116,33 @@ int ma_solver_get_field(ma_solver *S, int field, double *host) {
     default:
       return ma_set_error(MA_ERR_INVALID, "unknown field");
   }
+}
+
+int ma_solver_debug_array(ma_solver *S, const char *name, void *out, size_t capacity, size_t *size) {
+  if (!S || !name) return ma_set_error(MA_ERR_INVALID, "ma_solver_debug_array: null argument");
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  const std::string n = name;
+  const void *src = nullptr;
+  size_t bytes = 0;
+  const size_t n_cells = (size_t)S->n_owned + S->n_ghost;
+  if (n == "tiles") src = S->d_tiles, bytes = (size_t)S->n_tiles * sizeof(ma::TileInfoDev);
+  else if (n == "slot_face") src = S->d_slot, bytes = S->n_slot_entries * sizeof(uint16_t);
+  else if (n == "slot_nbr") src = S->d_slot_nbr, bytes = S->d_slot_nbr ? S->n_slot_entries * sizeof(uint16_t) : 0;
+  else if (n == "face_lr") src = S->d_face_lr, bytes = S->n_face_entries * sizeof(uint32_t);
+  else if (n == "tile_halo") src = S->d_tile_halo, bytes = S->n_halo_entries * sizeof(int);
+  else if (n == "tile_pub") src = S->d_tile_pub, bytes = S->d_tile_pub ? S->n_halo_entries * sizeof(int) : 0;
+  else if (n == "old2new") src = S->d_old2new, bytes = n_cells * sizeof(int);
+  else if (n == "face_geom") src = S->d_geom, bytes = S->n_geom_entries * sizeof(double);
+  else if (n == "cell_xyz") src = S->d_xyz, bytes = (size_t)3 * S->stride * sizeof(double);
+  else if (n == "cell_vol") src = S->d_vol, bytes = (size_t)S->stride * sizeof(double);
+  else if (n == "topology_on_device") bytes = S->topology_on_device ? 1 : 0;
+  else return ma_set_error(MA_ERR_INVALID, "ma_solver_debug_array: unknown array '" + n + "'");
+  if (size) *size = bytes;
+  if (out && src && bytes) {
+    MA_CUDA_TRY(cudaStreamSynchronize(S->st));
+    MA_CUDA_TRY(cudaMemcpy(out, src, std::min(bytes, capacity), cudaMemcpyDeviceToHost));
+  }
+  return MA_OK;
 }
 
 int ma_solver_get_timing(ma_solver *S, ma_timing *t) {

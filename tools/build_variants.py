@@ -90,8 +90,9 @@ def build_one(tag):
     for i, ln in enumerate(lines):
         if "Function properties" in ln and "flux_rk_tma_kernelILb1ELb1ENS_7TileCapILi128" in ln:
             info = [lines[i + 1].strip(), lines[i + 2].strip()]
-    objs = [obj] + [extra_objs.get(n, os.path.join(B.BUILD, n)) for n in ("kernels_strict.o", "geom_kernels.o", "solver.o", "host_common.o",
-                                                                        "host_mesh.o", "layout.o", "comm.o", "host_report.o")]
+    objs = [obj] + [extra_objs.get(n, os.path.join(B.BUILD, n)) for n in ("kernels_strict.o", "geom_kernels.o", "solver.o", "topology_kernels.o",
+                                                                        "host_common.o", "host_mesh.o", "layout.o", "comm.o",
+                                                                        "host_report.o")]
     p = subprocess.run([nvcc] + B.ARCH + ["-shared", "-o", lib] + objs + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl"],
                        capture_output=True, text=True)
     if p.returncode != 0:
