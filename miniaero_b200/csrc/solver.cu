@@ -527,6 +527,19 @@ void ma_solver_destroy(ma_solver *S) {
   delete S;
 }
 
+// MINIAERO_LAYOUT_TIMING=1: where the set-up time goes (stderr)
+struct SetupLap {
+  bool on = getenv("MINIAERO_LAYOUT_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void operator()(const char *what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "setup: %-34s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
+
 // common front end of the two constructors: configuration checks and the tile size
 static int create_prologue(const ma_options *opt, const ma_solver_config *cfg_in, ma_solver_config &cfg, int td[3]) {
   if (cfg_in)
@@ -611,8 +624,10 @@ int ma_solver_create_structured(const ma_options *opt, int rank, int num_ranks, 
                         !(fv && !strcmp(fv, "gather"));
     if (wanted) {
       ma::TopoPlan plan;
+      SetupLap lap;
       rc = ma::build_topology_plan(*opt, rank, num_ranks, td, share, L, &grid, plan);
       if (rc) return rc;
+      lap("topology plan (host)");
       if (ma_fast::pick_tile_class(L.max_tile_cells_real, L.max_tile_faces, L.max_tile_halo) >= 0)
         return solver_from_layout(L, &grid, opt, cfg, out, &plan);
     }
@@ -707,6 +722,7 @@ static int build_topology_on_device(ma_solver *S, const ma::HostLayout &L, const
 static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid, const ma_options *opt,
                               const ma_solver_config &cfg, ma_solver **out, const ma::TopoPlan *plan) {
   int rc = MA_OK;
+  SetupLap lap;
   ma_solver *S = new ma_solver();
   std::memset(&S->tm, 0, sizeof(S->tm));
   std::memset(&S->dm, 0, sizeof(S->dm));
@@ -765,6 +781,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
   MA_CU(cudaEventCreate(&S->ev_t0));
   MA_CU(cudaEventCreate(&S->ev_t1));
 
+  lap("streams, events");
   // ---- upload the layout
   {
     std::vector<ma::TileInfoDev> tiles(L.tiles.size());
@@ -788,8 +805,10 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
     int *d_new2old = nullptr;
     size_t scratch = 0;
     int r2 = MA_OK;
+    lap("geometry arrays allocated");
     if (plan) {  // the topology itself is built on the device: face codes and the cell permutation are already there
       r2 = build_topology_on_device(S, L, *grid, *plan, &d_code, &d_new2old);
+      lap("topology on the device");
     } else {
       r2 = dev_upload(&d_code, L.face_code, &scratch);
       if (!r2) r2 = dev_upload(&d_new2old, L.new2old, &scratch);
@@ -812,6 +831,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
       return r2;
     }
     MA_CU(ge);
+    lap("geometry on the device");
     std::vector<uint32_t>().swap(L.face_code);
   } else {
     MA_TRY(dev_upload(&S->d_xyz, L.cell_xyz, &S->device_bytes));
@@ -919,6 +939,7 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
       S->grad_threads = 128;
     }
   }
+  lap("remaining uploads, state arrays");
   S->tm.device_bytes = S->device_bytes;
   S->tm.num_tiles = S->n_tiles;
   S->tm.tile_faces_total = (int)std::min<long>(L.n_tile_faces_real, 2147483647L);
