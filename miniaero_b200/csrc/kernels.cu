@@ -1263,6 +1263,25 @@ __global__ void primitives_kernel(const DevMesh m, const double *__restrict__ Un
   for (int k = 0; k < 5; ++k) V[(size_t)k * m.stride + c] = P[k];
 }
 
+// caller order AoS [n_owned][5] conservative state -> Un (SoA, renumbered) and its primitives V, one thread per cell:
+// ma_solver_set_solution / ma_solver_submit (the 40 contiguous bytes of a cell are read by one thread; cells of a
+// z-line are neighbours in both numberings, so the five component stores of a warp fall into few sectors)
+__global__ void set_state_kernel(const DevMesh m, const double *__restrict__ aos, const int *__restrict__ old2new,
+                                 double *__restrict__ Un, double *__restrict__ V) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= m.n_owned) return;
+  double U[5], P[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) U[k] = aos[(size_t)5 * c + k];
+  compute_primitives(U, P);
+  const int n = old2new[c];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    Un[(size_t)k * m.stride + n] = U[k];
+    V[(size_t)k * m.stride + n] = P[k];
+  }
+}
+
 __global__ void initial_conditions_kernel(const DevMesh m, double *__restrict__ Un, int sod, double midx,
                                           double s1_rho, double s1_rhoE, double s2_rho, double s2_rhoE) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1570,6 +1589,12 @@ cudaError_t launch_flux_rk(const DevMesh &m, const StageArgs &a, bool second, bo
 cudaError_t launch_primitives(const DevMesh &m, const double *Un, double *V, cudaStream_t st) {
   const int threads = 256;
   primitives_kernel<<<(m.n_owned + threads - 1) / threads, threads, 0, st>>>(m, Un, V);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_state(const DevMesh &m, const double *aos, const int *old2new, double *Un, double *V, cudaStream_t st) {
+  const int threads = 256;
+  set_state_kernel<<<(m.n_owned + threads - 1) / threads, threads, 0, st>>>(m, aos, old2new, Un, V);
   return cudaGetLastError();
 }
 

@@ -78,6 +78,9 @@ struct StageArgs {
   int tile_class_threads(int tile_class, int which);                                                                 \
   /* GasModel.h:70-90 over the owned cells: conservative Un -> primitives V */                                       \
   cudaError_t launch_primitives(const ma::DevMesh &m, const double *Un, double *V, cudaStream_t st);                 \
+  /* caller-order AoS conservative state -> Un (renumbered SoA) and its primitives V in one pass */                  \
+  cudaError_t launch_set_state(const ma::DevMesh &m, const double *aos, const int *old2new, double *Un, double *V,   \
+                               cudaStream_t st);                                                                     \
   /* Initial_Conditions.h:38-133 */                                                                                  \
   cudaError_t launch_initial_conditions(const ma::DevMesh &m, double *Un, int problem_type, double midx,             \
                                         cudaStream_t st);                                                            \

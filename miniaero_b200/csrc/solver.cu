@@ -33,7 +33,7 @@ namespace {
   } while (0)
 
 // ---- layout-independent helper kernels -----------------------------------------------------------------
-// caller order AoS [n_owned][ncomp]  <->  device SoA [ncomp][stride] in renumbered order
+// device SoA [ncomp][stride] in renumbered order -> caller order AoS [n_owned][ncomp] (any field: get_field)
 __global__ void soa_to_caller_kernel(const double *__restrict__ soa, int stride, int ncomp, int n_owned,
                                      const int *__restrict__ old2new, double *__restrict__ out) {
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,12 +41,14 @@ __global__ void soa_to_caller_kernel(const double *__restrict__ soa, int stride,
   const int cell = (int)(i / ncomp), k = (int)(i % ncomp);
   out[i] = soa[(size_t)k * stride + old2new[cell]];
 }
-__global__ void caller_to_soa_kernel(const double *__restrict__ in, int stride, int ncomp, int n_owned,
-                                     const int *__restrict__ old2new, double *__restrict__ soa) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long)n_owned * ncomp) return;
-  const int cell = (int)(i / ncomp), k = (int)(i % ncomp);
-  soa[(size_t)k * stride + old2new[cell]] = in[i];
+// the conservative state, one thread per cell (five strided loads, 40 contiguous bytes stored)
+__global__ void state_to_caller_kernel(const double *__restrict__ soa, int stride, int n_owned,
+                                       const int *__restrict__ old2new, double *__restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_owned) return;
+  const int n = old2new[c];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) out[(size_t)5 * c + k] = soa[(size_t)k * stride + n];
 }
 // halo pack / unpack (CopyGhost.h:93-211): buf[i][col0 + k] <-> field[k][ids[i]]
 __global__ void pack_kernel(const double *__restrict__ field, int stride, int ncomp, const int *__restrict__ ids,
@@ -158,15 +160,16 @@ struct Api {
   decltype(&ma_fast::flux_smem_bytes) flux_smem;
   decltype(&ma_fast::launch_initial_conditions) ic;
   decltype(&ma_fast::launch_primitives) prims;
+  decltype(&ma_fast::launch_set_state) set_state;
 };
 Api api_of(bool strict) {
   if (strict)
     return {&ma_strict::launch_grad_limiter, &ma_strict::launch_flux_rk, &ma_strict::flux_rk_prepare,
             &ma_strict::grad_smem_bytes, &ma_strict::flux_smem_bytes,
-            &ma_strict::launch_initial_conditions, &ma_strict::launch_primitives};
+            &ma_strict::launch_initial_conditions, &ma_strict::launch_primitives, &ma_strict::launch_set_state};
   return {&ma_fast::launch_grad_limiter, &ma_fast::launch_flux_rk, &ma_fast::flux_rk_prepare,
           &ma_fast::grad_smem_bytes, &ma_fast::flux_smem_bytes,
-          &ma_fast::launch_initial_conditions, &ma_fast::launch_primitives};
+          &ma_fast::launch_initial_conditions, &ma_fast::launch_primitives, &ma_fast::launch_set_state};
 }
 
 int check_device(int device) {
@@ -1064,7 +1067,6 @@ int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, in
   const int slot = (int)(P.submitted & 1);
   const bool reuse = P.submitted >= 2;
   const int threads = 256;
-  const unsigned blocks = (unsigned)((elems + threads - 1) / threads);
   // upload (copy-in stream)
   if (reuse) MA_CUDA_TRY(cudaStreamWaitEvent(P.cin, P.in_free[slot], 0));
   MA_CUDA_TRY(cudaMemcpyAsync(P.d_in[slot], state_in, elems * sizeof(double), cudaMemcpyHostToDevice, P.cin));
@@ -1073,10 +1075,8 @@ int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, in
   int rc = wait_state_exchange(S);
   if (rc) return rc;
   MA_CUDA_TRY(cudaStreamWaitEvent(S->st, P.in_ready[slot], 0));
-  caller_to_soa_kernel<<<blocks, threads, 0, S->st>>>(P.d_in[slot], S->stride, 5, S->n_owned, S->d_old2new, S->d_Un);
-  MA_CUDA_TRY(cudaGetLastError());
+  MA_CUDA_TRY(K.set_state(S->dm, P.d_in[slot], S->d_old2new, S->d_Un, S->d_V[S->vcur], S->st));
   MA_CUDA_TRY(cudaEventRecord(P.in_free[slot], S->st));
-  MA_CUDA_TRY(K.prims(S->dm, S->d_Un, S->d_V[S->vcur], S->st));
   rc = start_state_exchange(S, S->d_V[S->vcur]);
   if (rc) return rc;
   for (int it = 0; it < nsteps; ++it) {
@@ -1086,7 +1086,8 @@ int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, in
   rc = wait_state_exchange(S);
   if (rc) return rc;
   if (reuse) MA_CUDA_TRY(cudaStreamWaitEvent(S->st, P.out_free[slot], 0));
-  soa_to_caller_kernel<<<blocks, threads, 0, S->st>>>(S->d_Un, S->stride, 5, S->n_owned, S->d_old2new, P.d_out[slot]);
+  state_to_caller_kernel<<<(unsigned)((S->n_owned + threads - 1) / threads), threads, 0, S->st>>>(
+      S->d_Un, S->stride, S->n_owned, S->d_old2new, P.d_out[slot]);
   MA_CUDA_TRY(cudaGetLastError());
   MA_CUDA_TRY(cudaEventRecord(P.out_ready[slot], S->st));
   // download (copy-out stream)
@@ -1096,13 +1097,25 @@ int ma_solver_submit(ma_solver *S, const double *state_in, double *state_out, in
   P.submitted++;
   S->tm.steps += nsteps;
   S->tm.cell_updates += (long long)nsteps * S->n_owned;
-  S->tm.kernel_launches += 3;
+  S->tm.kernel_launches += 2;
   return MA_OK;
 }
 
 int ma_solver_get_solution(ma_solver *S, double *host) {
   if (!S || !host) return ma_set_error(MA_ERR_INVALID, "ma_solver_get_solution: null argument");
-  return download_field(S, S->d_Un, 5, host);
+  MA_CUDA_TRY(cudaSetDevice(S->device));
+  int rc = wait_state_exchange(S);
+  if (rc) return rc;
+  const size_t elems = (size_t)S->n_owned * 5;
+  rc = ensure_staging(S, elems);
+  if (rc) return rc;
+  const int threads = 256;
+  state_to_caller_kernel<<<(unsigned)((S->n_owned + threads - 1) / threads), threads, 0, S->st>>>(
+      S->d_Un, S->stride, S->n_owned, S->d_old2new, S->d_stage);
+  MA_CUDA_TRY(cudaGetLastError());
+  MA_CUDA_TRY(cudaMemcpyAsync(host, S->d_stage, elems * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+  MA_CUDA_TRY(cudaStreamSynchronize(S->st));
+  return MA_OK;
 }
 
 int ma_solver_set_solution(ma_solver *S, const double *host) {
@@ -1114,11 +1127,7 @@ int ma_solver_set_solution(ma_solver *S, const double *host) {
   rc = ensure_staging(S, elems);
   if (rc) return rc;
   MA_CUDA_TRY(cudaMemcpyAsync(S->d_stage, host, elems * sizeof(double), cudaMemcpyHostToDevice, S->st));
-  const int threads = 256;
-  caller_to_soa_kernel<<<(unsigned)((elems + threads - 1) / threads), threads, 0, S->st>>>(
-      S->d_stage, S->stride, 5, S->n_owned, S->d_old2new, S->d_Un);
-  MA_CUDA_TRY(cudaGetLastError());
-  MA_CUDA_TRY(api_of(S->strict).prims(S->dm, S->d_Un, S->d_V[S->vcur], S->st));
+  MA_CUDA_TRY(api_of(S->strict).set_state(S->dm, S->d_stage, S->d_old2new, S->d_Un, S->d_V[S->vcur], S->st));
   return start_state_exchange(S, S->d_V[S->vcur]);
 }
 
