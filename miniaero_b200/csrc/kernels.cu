@@ -2,7 +2,8 @@
 //   ma_fast   : -fmad=true  (production)
 //   ma_strict : -fmad=false -DMA_STRICT (bit-for-bit with the reference's -DCELL_FLUX build)
 //
-// Two kernels per RK stage, one CTA per tile of cells:
+// Two kernels per RK stage, one CTA per tile of cells (the flux kernel is launched once per pass when cut faces are
+// shared between tiles, layout.h):
 //   grad_limiter_kernel : thread per cell.  Green-Gauss gradient (GreenGauss.h:51-270), stencil
 //                         min/max (StencilLimiter.h:56-282) and Venkatakrishnan limiter
 //                         (StencilLimiter.h:356-500, VenkatLimiter.h:45-73) gathered over the cell's six
@@ -42,18 +43,7 @@ MA_DEV void cp_async8(double *smem_dst, const double *gmem_src) {
 }
 MA_DEV void cp_async_commit_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-// Shared cut faces order a tile group as [first flux pass | second pass] — the two colours of the tile lattice's
-// checkerboard, each in Morton order — so the i-th tile of either pass is one half of the i-th Morton pair.  The
-// gradient sweep has no passes: it walks the group pair by pair (first[0], second[0], first[1], second[1], ...), i.e.
-// in (nearly) the Morton order of the whole group, and the neighbour cells it gathers are again the ones the tiles
-// just before it staged.  n_first == ntiles (or 0): plain order.
-MA_DEV int interleaved_tile(int b, int n_first, int ntiles) {
-  const int n_second = ntiles - n_first;
-  const int paired = n_first < n_second ? n_first : n_second;
-  if (b < 2 * paired) return (b & 1) ? n_first + (b >> 1) : (b >> 1);
-  const int rem = b - 2 * paired;
-  return n_first > n_second ? paired + rem : n_first + paired + rem;
-}
+using ma::interleaved_tile;
 
 MA_DEV void load_state(const double *__restrict__ base, int stride, int c, double (&v)[5]) {
 #pragma unroll

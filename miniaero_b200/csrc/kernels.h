@@ -46,6 +46,23 @@ struct DevMesh {
   double inflow[5];                    // TimeSolverExplicitRK4.h:218-223
 };
 
+// Shared cut faces order a tile group as [first flux pass | second pass] — the two colours of the tile lattice's
+// checkerboard, each in Morton order — so the i-th tile of either pass is one half of the i-th Morton pair.  The
+// gradient sweep has no passes: it walks the group pair by pair (first[0], second[0], first[1], second[1], ...), i.e.
+// in (nearly) the Morton order of the whole group, and the neighbour cells it gathers are again the ones the tiles
+// just before it staged.  n_first == ntiles (or 0): plain order.  A permutation of [0, ntiles) for every n_first
+// (tools/layout_check.cpp checks it).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int interleaved_tile(int b, int n_first, int ntiles) {
+  const int n_second = ntiles - n_first;
+  const int paired = n_first < n_second ? n_first : n_second;
+  if (b < 2 * paired) return (b & 1) ? n_first + (b >> 1) : (b >> 1);
+  const int rem = b - 2 * paired;
+  return n_first > n_second ? paired + rem : n_first + paired + rem;
+}
+
 struct StageArgs {
   const double *V;     // primitives (rho,u,v,w,T) of the stage state, every cell a tile touches ("solution_temp")
   double *Vnext;       // primitives of the next stage state (for the last stage: of the new solution)

@@ -17,7 +17,7 @@ def checker(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("layout") / "layout_check")
     objs = [os.path.join(b.BUILD, n) for n in ("layout.o", "host_mesh.o", "host_common.o")]
     subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-I" + os.path.join(ROOT, "include"), "-I" + b.CSRC,
-                    os.path.join(ROOT, "tools", "layout_check.cpp")] + objs + ["-o", exe], check=True)
+                    "-I" + b._cuda_include(), os.path.join(ROOT, "tools", "layout_check.cpp")] + objs + ["-o", exe], check=True)
     return exe
 
 

@@ -10,6 +10,7 @@
 #include <map>
 #include <vector>
 
+#include "kernels.h"
 #include "layout.h"
 #include "miniaero_b200.h"
 
@@ -129,6 +130,19 @@ int main(int argc, char **argv) {
            evals, mesh->internal_faces.nfaces, twice, imports, L.launch_count[0], L.launch_count[1], L.launch_count[2],
            L.launch_count[3]);
   }
+  // the gradient sweep's walk through a tile group (interleaved_tile): a permutation for every split, pairs first
+  for (int ntiles : {0, 1, 2, 7, 64, L.launch_count[0] + L.launch_count[1]})
+    for (int n_first : {0, 1, ntiles / 2, (ntiles + 1) / 2, ntiles - 1, ntiles, L.launch_count[0]}) {
+      if (n_first < 0 || n_first > ntiles) continue;
+      std::vector<char> hit((size_t)ntiles, 0);
+      for (int b = 0; b < ntiles; ++b) {
+        const int t = ma::interleaved_tile(b, n_first, ntiles);
+        if (t < 0 || t >= ntiles || hit[t]) { ++bad; break; }
+        hit[t] = 1;
+        const int paired = std::min(n_first, ntiles - n_first);
+        if (b < 2 * paired && t != ((b & 1) ? n_first + b / 2 : b / 2)) ++bad;
+      }
+    }
   printf("invariant violations: %ld\n", bad);
   // ---- wavefront model of the staged flux kernel
   long ideal1 = 0, wf1 = 0, ideal2 = 0, wf2 = 0, paths = 0, warps = 0;
