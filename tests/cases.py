@@ -25,6 +25,11 @@ EXTRA = {
     "sod_o1_visc": _inp(0, 0.3048, 1.0, 1.0, 0.0, 64, 4, 4, 100, 2e-6, 0, 1),
     "flatplate_o1": _inp(1, 2.0, 0.002, 1.0, 0.0, 16, 32, 2, 100, 3e-8, 0, 0),   # NoSlip stays viscous (…RK4.h:457-460)
     "ramp_odd": _inp(2, 1.7, 0.9, 1.3, 17.0, 13, 7, 5, 100, 1e-5, 1, 1),         # ragged sizes: partial tiles
+    # degenerate meshes: a single cell (six boundary faces, no internal face), a pair, a pencil, a one-cell-thick slab
+    "one_cell": _inp(0, 0.3048, 1.0, 1.0, 0.0, 1, 1, 1, 100, 2e-6, 1, 1),
+    "two_cells": _inp(0, 0.3048, 1.0, 1.0, 0.0, 2, 1, 1, 100, 2e-6, 1, 1),
+    "pencil_z": _inp(1, 2.0, 0.002, 1.0, 0.0, 1, 1, 5, 100, 1e-8, 1, 1),
+    "slab_o1": _inp(2, 2.0, 2.0, 1.0, 30.0, 3, 1, 2, 100, 1e-5, 0, 0),
 }
 
 
