@@ -574,6 +574,9 @@ using Cap64 = TileCap<64, 240, 96, 64, 6, 8, 96, 6>;      // 4x4x4 bricks
 #ifndef MA_C128_GB1
 #define MA_C128_GB1 4
 #endif
+#ifndef MA_GRAD_STAGE_CELL
+#define MA_GRAD_STAGE_CELL 1
+#endif
 using Cap128 = TileCap<128, 464, 160, 128, 3, MA_C128_GB1, MA_C128_FT, MA_C128_FB>;  // 4x4x8 / 8x4x4 bricks (flux: 160 threads = one per cut face, 464 faces in three rounds; 20 warps per SM at 94 registers, no spills)
 #ifndef MA_C256_FB
 #define MA_C256_FB 1
@@ -701,8 +704,15 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NG = GDIRECT ? 0 : (SECOND ? 6 : 3);  // staged geometry components: normal (+ centroid)
   constexpr int NGC = SECOND ? 6 : 3;                 // geometry components the arithmetic reads
-  constexpr int FC = CAP::FC, LS = CAP::LS;
-  constexpr int STAGE = NG * FC + 5 * LS;  // doubles per stage: sG[NG][FC], sV[5][LS]
+  constexpr int FC = CAP::FC, LS = CAP::LS, RC = CAP::RC, SC = CAP::SC;
+  // MA_GRAD_STAGE_CELL (default 1): the per-cell operands (slot maps, volume, centroid) arrive with the bulk copies
+  // instead of by sixteen per-thread global loads: sC[1 + NXC][RC] (volume, centroid), sS[12][SC] (slot_face, slot_nbr;
+  // 16-bit).  41 KB per CTA instead of 34 (still four CTAs per SM, the register file is the limit), 126 registers and
+  // no spill instead of 128 with 24 bytes spilled; 6.47 -> 6.10 ms at 67 M cells (profiles/r02d_variants.md §6)
+  constexpr bool SCELL = MA_GRAD_STAGE_CELL != 0;
+  constexpr int NXC = SECOND ? 3 : 0;
+  constexpr int CELL_D = SCELL ? (1 + NXC) * RC + (12 * SC * 2 + 7) / 8 : 0;
+  constexpr int STAGE = NG * FC + 5 * LS + CELL_D;  // doubles per stage: sG[NG][FC], sV[5][LS] (, sC, sS)
   constexpr int HPT = (CAP::HC + CAP::GRAD_THREADS - 1) / CAP::GRAD_THREADS;  // outside cells per thread
   double *sbase = reinterpret_cast<double *>(smem_raw) + 2;  // two mbarriers, then the stages
   const unsigned bar0 = smem_addr(smem_raw);
@@ -742,7 +752,9 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
     const unsigned fcp = (unsigned)(T.face_count + 15) & ~15u;
     if (tid < 32) {
       const unsigned gbytes = fcp * 8u, vbytes = (unsigned)hb * 8u;
-      if (tid == 0) mbar_arrive_expect_tx(bar, NG * gbytes + 5 * vbytes);
+      const int ssh = T.cell_start & 7;
+      const unsigned sbytes = (unsigned)((ssh + T.cell_count + 7) & ~7) * 2u;
+      if (tid == 0) mbar_arrive_expect_tx(bar, NG * gbytes + 5 * vbytes + (SCELL ? (1 + NXC) * vbytes + 12 * sbytes : 0u));
       __syncwarp();
       // generic-proxy reads of this stage (ordered before by the CTA barrier) precede the copy engine's writes
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -752,6 +764,16 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
         bulk_g2s(smem_addr(sG + tid * FC), m.face_geom + (size_t)6 * T.face_start + (size_t)tid * fcp, gbytes, bar);
       else if (tid < NG + 5)
         bulk_g2s(smem_addr(sV + (tid - NG) * LS), V_ + (size_t)(tid - NG) * m.stride + (T.cell_start - shift), vbytes, bar);
+      else if (SCELL && tid < NG + 5 + 1 + NXC) {
+        const int j = tid - (NG + 5);
+        const double *base = j == 0 ? m.cell_vol : m.cell_xyz + (size_t)(j - 1) * m.stride;
+        bulk_g2s(smem_addr(sV + 5 * LS + j * RC), base + (T.cell_start - shift), vbytes, bar);
+      } else if (SCELL && tid < NG + 5 + 1 + NXC + 12) {
+        const int q = tid - (NG + 5 + 1 + NXC);
+        const unsigned short *base = q < 6 ? m.slot_face + (size_t)q * m.slot_stride : m.slot_nbr + (size_t)(q - 6) * m.slot_stride;
+        unsigned short *sS = reinterpret_cast<unsigned short *>(sV + 5 * LS + (1 + NXC) * RC);
+        bulk_g2s(smem_addr(sS + q * SC), base + (T.cell_start - ssh), sbytes, bar);
+      }
     }
 #pragma unroll
     for (int j = 0; j < HPT; ++j) {
@@ -769,6 +791,7 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
     double vol, xc[3];
   };
   auto load_cell = [&](const TileInfoDev &T, CellRegs &r) {
+    if (SCELL) return;  // read from the stage after the wait
     const int c = T.cell_start + (tid < T.cell_count ? tid : 0);
 #pragma unroll
     for (int s = 0; s < 6; ++s)
@@ -797,6 +820,16 @@ __global__ void __launch_bounds__(CAP::GRAD_THREADS, (PERSIST && !GDIRECT) ? CAP
       if (t + 3 * G < ntiles) T3 = tiles[tix(t + 3 * G)];  // consumed two iterations from now
     }
     mbar_wait(bar0 + 8 * st, (unsigned)(i >> 1) & 1u);
+    if (SCELL && tid < T0.cell_count) {
+      const double *sC = sbase + st * STAGE + NG * FC + 5 * LS;
+      const unsigned short *sS = reinterpret_cast<const unsigned short *>(sC + (1 + NXC) * RC);
+      const int p = (T0.cell_start & 1) + tid, q = (T0.cell_start & 7) + tid;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) cur.sn[s] = (unsigned)sS[s * SC + q] | ((unsigned)sS[(6 + s) * SC + q] << 16);
+      cur.vol = sC[p];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) cur.xc[d] = SECOND ? sC[(1 + d) * RC + p] : 0.0;
+    }
     if (tid < T0.cell_count) {
       const double *sG = sbase + st * STAGE, *sV = sG + NG * FC;
       if (GDIRECT)
@@ -1400,7 +1433,8 @@ template <class CAP>
 static size_t grad_tma_smem(bool second) {  // one or two stages + two mbarriers
   const int mode = grad_persistent();
   const int ng = mode == 2 ? 0 : (second ? 6 : 3);
-  return (size_t)(mode ? 2 : 1) * (ng * CAP::FC + 5 * CAP::LS) * 8 + 16;
+  const int cell_d = MA_GRAD_STAGE_CELL ? (1 + (second ? 3 : 0)) * CAP::RC + (12 * CAP::SC * 2 + 7) / 8 : 0;
+  return (size_t)(mode ? 2 : 1) * (ng * CAP::FC + 5 * CAP::LS + cell_d) * 8 + 16;
 }
 // grid of a persistent kernel: resident CTAs per SM x SMs of the current device
 static int persistent_ctas(int ctas_per_sm) {

@@ -37,6 +37,8 @@ VARIANTS = {
     "c256b2": ["-DMA_C256_FB=2"],
     "t128b3p": ["-DMA_FLUX_PREFETCH_AHEAD=444"] + OLD,
     "g5": ["-DMA_C128_GB1=5"],
+    "gsc0": ["-DMA_GRAD_STAGE_CELL=0"],
+    "gsc1": ["-DMA_GRAD_STAGE_CELL=1"],   # gradient kernel: slot maps, volume, centroid arrive with the bulk copies
     "xg_copyonly": ["-DMA_GRAD_EXPERIMENT=1"],
     "xg_computeonly": ["-DMA_GRAD_EXPERIMENT=2"],
     "x_copyonly": ["-DMA_FLUX_EXPERIMENT=1"],
