@@ -677,16 +677,25 @@ def gpu_arm(args):
         torch.cuda.empty_cache()
         so = workload_options("flatplate_strong", world)
         need = 600.0 * so["nx"] * so["ny"] * so["nz"] / world   # ~575 B/cell of device memory
-        free_dev = torch.cuda.mem_get_info()[0]
+        free_dev = -max_over_ranks(-float(torch.cuda.mem_get_info()[0]))   # the least over the ranks: one decision for all
         if need > 0.95 * free_dev:
             strong = {"skipped": "%.0f GB per GPU needed, %.0f GB free" % (need / 1e9, free_dev / 1e9)}
         else:
             per_rank4 = (320.0 if args.mesh_path == "structured" else 900.0) * so["nx"] * so["ny"] * so["nz"] / world
             group4 = int(max(1, min(world, avail * 0.8 // max(per_rank4, 1.0))))
+            s4, err4 = None, None
             for g0 in range(0, world, group4):
                 if g0 <= rank < g0 + group4:
-                    s4, _, i4 = build_solver(ma, so, rank, world, comm, local_rank, mesh_path=args.mesh_path)
+                    try:
+                        s4, _, i4 = build_solver(ma, so, rank, world, comm, local_rank, mesh_path=args.mesh_path)
+                    except RuntimeError as ex:   # out of memory on this rank: the leg is dropped on every rank, not the line
+                        err4 = str(ex)[:200]
                 barrier()
+            if max_over_ranks(1.0 if err4 else 0.0) > 0.0:
+                strong = {"failed": err4 or "another rank could not build its block"}
+                s4 = None
+                torch.cuda.empty_cache()
+        if strong is None:
             t4 = time_steps(s4, max(3, args.steps // 2), 3, barrier)
             st4 = max_over_ranks(t4["step_seconds"])
             cells4 = so["nx"] * so["ny"] * so["nz"]

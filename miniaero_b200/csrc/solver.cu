@@ -362,14 +362,19 @@ int one_step(ma_solver *S, const Api &K) {
   S->sim_time += S->opt.dt;  // TimeSolverExplicitRK4.h:343
   S->time_it++;
   const bool graph_ok = S->use_graph && S->n_ghost == 0 && !S->profiling && !S->u_pending;
-  if (!graph_ok) {
-    for (int k = 0; k < 4; ++k) {
-      int rc = run_stage(S, K, k);
-      if (rc) return rc;
-    }
-    return MA_OK;
-  }
   const int par = S->vcur;
+  // a step whose launches fail did not happen: the clock and the stage-buffer parity go back to where they were
+  auto direct = [&]() {
+    int rc = MA_OK;
+    for (int k = 0; k < 4 && !rc; ++k) rc = run_stage(S, K, k);
+    if (rc) {
+      S->sim_time -= S->opt.dt;
+      S->time_it--;
+      S->vcur = par;
+    }
+    return rc;
+  };
+  if (!graph_ok) return direct();
   if (!S->step_graph[par]) {
     const long long before = S->tm.kernel_launches;
     cudaGraph_t g = nullptr;
@@ -389,15 +394,7 @@ int one_step(ma_solver *S, const Api &K) {
       if (g) cudaGraphDestroy(g);
       cudaGetLastError();
       S->use_graph = false;
-      for (int k = 0; k < 4; ++k) {
-        rc = run_stage(S, K, k);
-        if (rc) break;
-      }
-      if (rc) {  // the step did not happen
-        S->sim_time -= S->opt.dt;
-        S->time_it--;
-      }
-      return rc;
+      return direct();
     }
     const cudaError_t ie = cudaGraphInstantiate(&S->step_graph[par], g, 0);
     cudaGraphDestroy(g);
