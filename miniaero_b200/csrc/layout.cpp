@@ -722,8 +722,8 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   lap("tiles + renumbering");
   // ---- 4. cell SoA
   if (!defer_geometry) {
-    L.cell_xyz.assign((size_t)3 * L.stride, 0.0);
-    L.cell_vol.assign((size_t)L.stride, 1.0);
+    big_assign(L.cell_xyz, (size_t)3 * L.stride, 0.0);
+    big_assign(L.cell_vol, (size_t)L.stride, 1.0);
   }
 #pragma omp parallel for schedule(static)
   for (long c = 0; c < (defer_geometry ? 0 : n_cells); ++c) {
@@ -739,7 +739,7 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   // (or by its only in-tile cell), in (cell, slot) order: the flux sweep then walks cells in order
   // and every cell's data is touched within a short window.
   L.slot_stride = round_up(n_owned, 32);
-  L.slot_face.assign((size_t)6 * L.slot_stride, 0);
+  big_assign(L.slot_face, (size_t)6 * L.slot_stride, (uint16_t)0);
   auto emits = [&](const TileInfo &T, int newc, int s) -> bool {
     const int oldc = L.new2old[newc];
     const int oth = mesh.info(oldc, s).other;
@@ -779,6 +779,7 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   };
   // structured blocks: tiles with the same key (StructuredAccess::tile_key) share one order
   std::unordered_map<uint64_t, std::shared_ptr<const TileOrder>> order_cache;
+  std::unordered_map<std::string, std::shared_ptr<const TileOrder>> sig_cache;
   std::mutex order_mutex;
   auto order_of = [&](const TileInfo &T) -> std::shared_ptr<const TileOrder> {
     uint64_t key = 0;
@@ -803,11 +804,39 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
       auto it = order_cache.find(key);
       if (it != order_cache.end()) return it->second;
     }
+    // No pattern key (a mesh handed over as arrays, an irregular tile): the order is a function of what the three
+    // callbacks of compute_tile_order answer — tiles that answer alike (nearly all of a mesh with any regularity)
+    // share one order.  The key is the answers themselves, so equal keys mean equal orders exactly.
+    std::string sig;
+    if (!key && T.cell_count <= 4096) {
+      sig.resize(8 + (size_t)24 * T.cell_count);
+      uint32_t *w = reinterpret_cast<uint32_t *>(&sig[0]);
+      w[0] = (uint32_t)T.cell_count, w[1] = (uint32_t)(T.cell_start & 1);
+      for (int lc = 0; lc < T.cell_count; ++lc)
+        for (int sl = 0; sl < 6; ++sl) {
+          const int c = T.cell_start + lc;
+          uint32_t v = 0;
+          if (emits(T, c, sl)) {
+            const int kind = cut_kind(T, c, sl);
+            const SlotInfo si = mesh.info(L.new2old[c], sl);
+            const int on = (si.other >= 0 && si.other < n_owned) ? L.old2new[si.other] : -1;
+            const int other_local = (on >= T.cell_start && on < T.cell_start + T.cell_count) ? on - T.cell_start : -1;
+            v = 1u | (uint32_t)kind << 1 | (uint32_t)si.side << 3 | (uint32_t)(other_local + 1) << 4;
+          }
+          w[2 + 6 * lc + sl] = v;
+        }
+      std::lock_guard<std::mutex> lock(order_mutex);
+      auto it = sig_cache.find(sig);
+      if (it != sig_cache.end()) return it->second;
+    }
     auto O = std::make_shared<TileOrder>();
     compute_order(T, *O);
-    if (key) {
+    if (key || !sig.empty()) {
       std::lock_guard<std::mutex> lock(order_mutex);
-      order_cache.emplace(key, O);
+      if (key)
+        order_cache.emplace(key, O);
+      else
+        sig_cache.emplace(std::move(sig), O);
     }
     return O;
   };
@@ -826,6 +855,7 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     max_local = std::max(max_local, round_up((T.cell_start & 1) + T.cell_count, 2) + cut);
     max_halo = std::max(max_halo, cut);
   }
+  lap("tile face orders");
   if (max_faces >= 16384) return ma_set_error(MA_ERR_INVALID, "tile has more than 16383 faces; use smaller tile_dims");
   if (max_local >= 0xFFF0 - 2) return ma_set_error(MA_ERR_INVALID, "tile has too many cells + cut faces; use smaller tile_dims");
   L.max_tile_faces = max_faces;
@@ -856,20 +886,21 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     L.n_import_areas = areas;
     L.import_capacity = round_up(cap, 2);
     if ((long)areas * 5 * L.import_capacity >= (1L << 31)) return ma_set_error(MA_ERR_INVALID, "more than 2^31 shared cut-face flux entries");
-    if (share) L.tile_pub.assign((size_t)n_tiles * L.halo_stride, -1);
+    if (share) big_assign(L.tile_pub, (size_t)n_tiles * L.halo_stride, -1);
   }
   const size_t NF = (size_t)L.n_tile_faces;
   if (defer_geometry)
-    L.face_code.assign(NF, 0);
+    big_assign(L.face_code, NF, (uint32_t)0);
   else
-    L.face_geom.assign((size_t)L.geom_components * NF, 0.0);
+    big_assign(L.face_geom, (size_t)L.geom_components * NF, 0.0);
   const int GX = with_tangents ? 9 : 3;  // first centroid component
   double frame_err = 0.0;
-  L.face_left.assign(NF, 0);
-  L.face_right.assign(NF, 0);
-  L.face_lr.assign(NF, 0);
-  L.slot_nbr.assign((size_t)6 * L.slot_stride, 0xFFFF);
-  L.tile_halo.assign((size_t)n_tiles * L.halo_stride, -1);
+  big_assign(L.face_left, NF, 0);
+  big_assign(L.face_right, NF, 0);
+  big_assign(L.face_lr, NF, (uint32_t)0);
+  big_assign(L.slot_nbr, (size_t)6 * L.slot_stride, (uint16_t)0xFFFF);
+  big_assign(L.tile_halo, (size_t)n_tiles * L.halo_stride, -1);
+  lap("face arrays allocated");
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : frame_err)
   for (long k = 0; k < n_tiles; ++k) {
     const TileInfo &T = L.tiles[k];
@@ -951,6 +982,7 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
   }
 
   L.max_frame_error = frame_err;
+  lap("tile face lists");
 
   if (share) {
     // where every evaluated cut face publishes its flux: the import slot of the same face in the tile on the other
@@ -981,7 +1013,7 @@ int build_layout_impl(Mesh &mesh, const int tile_dims_in[3], bool with_tangents,
     if (bad_pub) return ma_set_error(MA_ERR_INVALID, "shared cut faces: a published face is not in the importing tile's list (internal error)");
   }
 
-  lap("tile face lists");
+  lap("publish lists");
   // ---- 6. halo lists (renumbered), grouped by peer
   if (n_ghost > 0) {
     long so = 0, ro = 0;

@@ -6,12 +6,42 @@
 // cell_gradient_ / stored_{min,max,limiter}_ (Cells.h:70-71, StencilLimiter.h:525-527).
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <utility>
 #include <vector>
 
 #include "mesh_geom.h"
 #include "miniaero_b200.h"
 
 namespace ma {
+
+// The O(cells) arrays of the layout: a vector whose resize() leaves new elements uninitialised, so that the pages are
+// first touched — and filled — by all host threads (big_assign) instead of by one: at 67 M cells the serial
+// value-initialisation of these arrays was half of the host builder's time.
+template <class T>
+struct NoInitAllocator : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = NoInitAllocator<U>;
+  };
+  template <class U, class... A>
+  void construct(U *p, A &&...a) {
+    if constexpr (sizeof...(A) == 0)
+      ::new ((void *)p) U;
+    else
+      ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T>
+using BigVec = std::vector<T, NoInitAllocator<T>>;
+template <class T>
+void big_assign(BigVec<T> &v, size_t n, T value) {
+  v.clear();
+  v.resize(n);
+  T *p = v.data();
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; ++i) p[i] = value;
+}
 
 // Boundary faces are encoded in the tile-face "right cell" entry as -1 - ma_bc_type.
 inline int bc_code(int type) { return -1 - type; }
@@ -45,19 +75,19 @@ struct HostLayout {
   long n_tile_faces = 0;     // length of the tile-packed face arrays (with per-tile padding)
   long n_tile_faces_real = 0;
 
-  std::vector<int> new2old, old2new;  // owned + ghost cells
+  BigVec<int> new2old, old2new;  // owned + ghost cells
   std::vector<TileInfo> tiles;
 
   // cell SoA (renumbered): xyz[3][stride], vol[stride]
-  std::vector<double> cell_xyz, cell_vol;
+  BigVec<double> cell_xyz, cell_vol;
   // slot map: slot_face[s][cell] (owned cells only, stride = n_owned rounded up to 32):
   // bits 0..13 tile-local face index, bit 14 = 1 for a boundary face, bit 15 = 1 when the cell is elem2 (right)
-  std::vector<uint16_t> slot_face;
+  BigVec<uint16_t> slot_face;
   int slot_stride = 0;
 
   // neighbour map (FAST kernels): slot_nbr[s][cell] = position of the cell across slot s in the tile's staged cell
   // list (see face_lr), 0xFFFF for a boundary face
-  std::vector<uint16_t> slot_nbr;
+  BigVec<uint16_t> slot_nbr;
 
   // tile-packed face geometry.
   // with_tangents (STRICT arithmetic): global SoA, component g of tile face j at geom[g*n_tile_faces + j],
@@ -67,20 +97,20 @@ struct HostLayout {
   //                fcp = T.face_count rounded up to 16, g = 0-2 normal, 3-5 centroid
   int geom_components = 12;
   double max_frame_error = 0.0;  // worst deviation of (n^, t, b/|a|) from an orthonormal frame over all faces
-  std::vector<double> face_geom;
+  BigVec<double> face_geom;
   // structured path with device-side geometry (build_layout_structured, defer_geometry): face_geom, cell_xyz and
   // cell_vol stay empty; face_code[j] = (elem1 cell in the block's (n+2)^3 lattice) * 8 + elem1 local face says which
   // face tile face j is, and new2old which cell, for geom_kernels.cu to evaluate mesh_geom.h on the device
   bool geometry_deferred = false;
-  std::vector<uint32_t> face_code;
-  std::vector<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
+  BigVec<uint32_t> face_code;
+  BigVec<int> face_left, face_right;  // renumbered cell ids; right < 0 -> boundary code
   // tile-local connectivity: low 16 bits = left cell, high 16 bits = right cell, as POSITIONS in the tile's staged
   // cell list: own cell lc sits at (cell_start & 1) + lc (the staging copy starts at the even cell below
   // cell_start: 16-byte alignment of the bulk copies), the outside cell of cut face e at
   // halo_base + (e - cut_start) with halo_base = ((cell_start & 1) + cell_count) rounded up to even;
   // a boundary face has right = 0xFFFF - ma_bc_type
-  std::vector<uint32_t> face_lr;
-  std::vector<int> tile_halo;  // renumbered id of the outside cell of every cut face, halo_stride entries per tile
+  BigVec<uint32_t> face_lr;
+  BigVec<int> tile_halo;  // renumbered id of the outside cell of every cut face, halo_stride entries per tile
   int max_tile_local = 0;      // largest staged cell list of a tile (halo_base + cut faces)
   int max_tile_halo = 0;       // largest number of cut faces of a tile
   int halo_stride = 0;         // tile k's outside cells are tile_halo[k * halo_stride ...], padded with -1
@@ -96,7 +126,7 @@ struct HostLayout {
   int n_import_areas = 0;
   // [n_tiles][halo_stride], parallel to tile_halo: where evaluated cut face cut_start + q publishes its flux (index of
   // component 0 in the exchange buffer), -1: nowhere (the other side is a ghost, or evaluates the face itself)
-  std::vector<int> tile_pub;
+  BigVec<int> tile_pub;
 
   // true: only the O(tiles) members and the exchange lists below are filled; the O(cells) arrays are built on the
   // device from a TopoPlan (build_topology_plan)

@@ -78,8 +78,8 @@ int dev_alloc(T **p, size_t n, size_t *tally) {
   if (tally) *tally += n * sizeof(T);
   return MA_OK;
 }
-template <class T>
-int dev_upload(T **p, const std::vector<T> &v, size_t *tally) {
+template <class T, class A>
+int dev_upload(T **p, const std::vector<T, A> &v, size_t *tally) {
   int rc = dev_alloc(p, v.size(), tally);
   if (rc) return rc;
   if (!v.empty()) MA_CUDA_TRY(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -832,12 +832,12 @@ static int solver_from_layout(ma::HostLayout &L, const ma::StructuredGrid *grid,
     }
     MA_CU(ge);
     lap("geometry on the device");
-    std::vector<uint32_t>().swap(L.face_code);
+    ma::BigVec<uint32_t>().swap(L.face_code);
   } else {
     MA_TRY(dev_upload(&S->d_xyz, L.cell_xyz, &S->device_bytes));
     MA_TRY(dev_upload(&S->d_vol, L.cell_vol, &S->device_bytes));
     MA_TRY(dev_upload(&S->d_geom, L.face_geom, &S->device_bytes));
-    std::vector<double>().swap(L.face_geom);
+    ma::BigVec<double>().swap(L.face_geom);
   }
   if (!plan) {
     MA_TRY(dev_upload(&S->d_slot, L.slot_face, &S->device_bytes));

@@ -12,8 +12,8 @@
 #include "miniaero_b200.h"
 #include "topology_stamp.h"
 
-template <class T>
-static long diff(const char *name, const std::vector<T> &a, const std::vector<T> &b) {
+template <class T, class A, class B>
+static long diff(const char *name, const std::vector<T, A> &a, const std::vector<T, B> &b) {
   long bad = a.size() != b.size();
   if (!bad) bad = a.empty() ? 0 : memcmp(a.data(), b.data(), a.size() * sizeof(T)) != 0;
   if (bad) {
