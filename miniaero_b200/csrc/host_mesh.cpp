@@ -47,9 +47,9 @@ struct Gen : ma::GridGen {
   void build_tables(double lx, double ly, double lz, double tan_ramp) { tables.build(*this, lx, ly, lz, tan_ramp); }
 };
 
-struct FaceArrays {
-  std::vector<double> coords, normal, tangent, binormal;
-  std::vector<int> conn, slot;
+struct FaceArrays {  // every entry is written by the generator's parallel loops: no value-initialisation (BigVec)
+  ma::BigVec<double> coords, normal, tangent, binormal;
+  ma::BigVec<int> conn, slot;
   void resize(size_t n) {
     coords.resize(3 * n);
     normal.resize(3 * n);
@@ -76,8 +76,8 @@ struct FaceArrays {
 struct ma_mesh_storage {
   ma_mesh view;
   Block block;
-  std::vector<double> cell_xyz, cell_vol;
-  std::vector<int> global_ids;
+  ma::BigVec<double> cell_xyz, cell_vol;
+  ma::BigVec<int> global_ids;
   FaceArrays internal;
   FaceArrays bc[6];
   std::vector<int> send_count, recv_count, send_ids, recv_ids;
@@ -167,7 +167,9 @@ int ma_mesh_generate(const ma_options *opt, int rank, int num_ranks, ma_mesh_sto
     // ---- internal faces in creation order: cell c creates local face f when the neighbour across f
     // exists and has a larger id (MeshProcessor.C:54-120).  Boundary faces of ghost cells are dropped
     // (delete_ghosted_faces, MeshProcessor.C:173-186); ghost-ghost faces are kept, as in the reference.
-    std::vector<long> first((size_t)ncells + 1, 0);
+    ma::BigVec<long> first;
+    first.resize((size_t)ncells + 1);
+    first[0] = 0;
 #pragma omp parallel for schedule(static)
     for (long c = 0; c < ncells; ++c) {
       int i, j, k;

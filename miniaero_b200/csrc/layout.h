@@ -10,38 +10,11 @@
 #include <utility>
 #include <vector>
 
+#include "host_common.h"
 #include "mesh_geom.h"
 #include "miniaero_b200.h"
 
 namespace ma {
-
-// The O(cells) arrays of the layout: a vector whose resize() leaves new elements uninitialised, so that the pages are
-// first touched — and filled — by all host threads (big_assign) instead of by one: at 67 M cells the serial
-// value-initialisation of these arrays was half of the host builder's time.
-template <class T>
-struct NoInitAllocator : std::allocator<T> {
-  template <class U>
-  struct rebind {
-    using other = NoInitAllocator<U>;
-  };
-  template <class U, class... A>
-  void construct(U *p, A &&...a) {
-    if constexpr (sizeof...(A) == 0)
-      ::new ((void *)p) U;
-    else
-      ::new ((void *)p) U(std::forward<A>(a)...);
-  }
-};
-template <class T>
-using BigVec = std::vector<T, NoInitAllocator<T>>;
-template <class T>
-void big_assign(BigVec<T> &v, size_t n, T value) {
-  v.clear();
-  v.resize(n);
-  T *p = v.data();
-#pragma omp parallel for schedule(static)
-  for (long i = 0; i < (long)n; ++i) p[i] = value;
-}
 
 // Boundary faces are encoded in the tile-face "right cell" entry as -1 - ma_bc_type.
 inline int bc_code(int type) { return -1 - type; }
