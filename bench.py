@@ -490,6 +490,7 @@ def gpu_arm(args):
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 64 << 30
+    avail = -max_over_ranks(-float(avail))   # one figure for all ranks: the group size below must agree (barriers)
     per_rank = (320.0 if args.mesh_path == "structured" else 900.0) * optd["nx"] * optd["ny"] * optd["nz"] / world
     group = int(max(1, min(world, avail * 0.8 // max(per_rank, 1.0))))
     solver = None
