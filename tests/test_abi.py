@@ -80,3 +80,52 @@ def test_invalid_arguments(lib):
         ma.Parallel3DMesh(4, 4, 4, 1.0, 1.0, 1.0, 0, rank=0, num_ranks=3).fillMeshData()  # ranks must be 2^k
     with pytest.raises(AttributeError):
         ma.Options(no_such_field=1)
+
+
+def test_header_is_plain_c_and_a_c_caller_links(lib, tmp_path):
+    """The boundary is a C ABI: include/miniaero_b200.h compiles as strict C99 (no C++ types, no torch), a caller
+    written in C links against the library, and the struct sizes the C compiler sees are the ctypes mirror's.  On a box
+    without a GPU the solver constructor must fail with MA_ERR_CUDA and a message, not crash."""
+    import subprocess
+    from miniaero_b200 import _abi
+    import miniaero_b200.build as b
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "miniaero_b200.h"
+int main(void) {
+  ma_options opt;
+  ma_solver_config cfg;
+  ma_mesh_storage *mesh = NULL;
+  ma_solver *solver = NULL;
+  int rc;
+  ma_options_default(&opt);
+  ma_solver_config_default(&cfg);
+  opt.nx = 4, opt.ny = 3, opt.nz = 2;
+  printf("sizes %d %d %d %d %d\n", (int)sizeof(ma_options), (int)sizeof(ma_faces), (int)sizeof(ma_mesh),
+         (int)sizeof(ma_solver_config), (int)sizeof(ma_timing));
+  printf("abi %d\n", ma_abi_version());
+  if (ma_mesh_generate(&opt, 0, 1, &mesh) != MA_OK) return 2;
+  printf("cells %d faces %d\n", ma_mesh_view(mesh)->num_owned_cells, ma_mesh_view(mesh)->internal_faces.nfaces);
+  rc = ma_solver_create(ma_mesh_view(mesh), &opt, &cfg, &solver);
+  printf("create %d %s\n", rc, rc == MA_OK ? "" : ma_last_error());
+  if (rc == MA_OK) ma_solver_destroy(solver);
+  ma_mesh_free(mesh);
+  return 0;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(b.LIB)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-L" + libdir, "-lminiaero_b200", "-Wl,-rpath," + libdir], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = dict(line.split(" ", 1) for line in p.stdout.strip().splitlines())
+    sizes = [int(x) for x in out["sizes"].split()]
+    assert sizes == [C.sizeof(_abi.Options), C.sizeof(_abi.Faces), C.sizeof(_abi.Mesh), C.sizeof(_abi.SolverConfig),
+                     C.sizeof(_abi.Timing)]
+    assert out["abi"].strip() == "3"
+    assert out["cells"].strip() == "24 faces 46"   # 4x3x2 cells: 3*3*2 + 4*2*2 + 4*3*1 internal faces
+    import torch
+    if not torch.cuda.is_available():
+        assert out["create"].startswith("-2 ") and "CUDA" in out["create"]   # MA_ERR_CUDA
