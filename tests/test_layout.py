@@ -35,6 +35,22 @@ def test_layout_invariants(checker, args):
     _run(checker, args)
 
 
+@pytest.mark.parametrize("share", ["", "1"])
+@pytest.mark.parametrize("args", [(37, 21, 13), (64, 32, 32), (16, 9, 7, 3, 5, 2)])
+def test_layout_does_not_depend_on_the_thread_count(checker, args, share):
+    """The host builder runs its O(cells) loops in parallel, first-touches its arrays from all threads and shares face
+    orders between tiles through a cache filled concurrently: the arrays it hands to the device must be the same bytes
+    whatever the number of threads."""
+    sums = set()
+    for threads in ("1", "3", "8"):
+        env = {"OMP_NUM_THREADS": threads}
+        if share:
+            env["MINIAERO_CHECK_SHARE"] = "1"
+        out = _run(checker, args, env)
+        sums.add(re.search(r"layout checksum: ([0-9a-f]{16})", out).group(1))
+    assert len(sums) == 1, sums
+
+
 @pytest.mark.parametrize("args", [(64, 8, 8), (37, 21, 13), (37, 21, 13, 4, 4, 4), (16, 9, 7, 3, 5, 2), (5, 3, 2, 8, 8, 8),
                                   (128, 4, 4), (9, 9, 9, 16, 2, 2), (64, 32, 32)])
 def test_shared_cut_faces(checker, args):

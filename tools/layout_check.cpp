@@ -144,6 +144,19 @@ int main(int argc, char **argv) {
       }
     }
   printf("invariant violations: %ld\n", bad);
+  {  // every array of the layout in one number: the builder's result must not depend on the number of host threads
+    unsigned long long h = 1469598103934665603ULL;
+    auto mix = [&](const void *p, size_t bytes) {
+      const unsigned char *c = static_cast<const unsigned char *>(p);
+      for (size_t i = 0; i < bytes; ++i) h = (h ^ c[i]) * 1099511628211ULL;
+    };
+    auto vec = [&](const auto &v) {
+      if (!v.empty()) mix(v.data(), v.size() * sizeof(v[0]));
+    };
+    vec(L.new2old), vec(L.old2new), vec(L.tiles), vec(L.cell_xyz), vec(L.cell_vol), vec(L.slot_face), vec(L.slot_nbr);
+    vec(L.face_geom), vec(L.face_left), vec(L.face_right), vec(L.face_lr), vec(L.tile_halo), vec(L.tile_pub);
+    printf("layout checksum: %016llx\n", h);
+  }
   // ---- wavefront model of the staged flux kernel
   long ideal1 = 0, wf1 = 0, ideal2 = 0, wf2 = 0, paths = 0, warps = 0;
   for (int k = 0; k < L.n_tiles; ++k) {
