@@ -257,6 +257,7 @@ class TimeSolverExplicitRK4:
 
     def synchronize(self):
         _abi.check(self._lib.ma_solver_synchronize(self._handle))
+        self._inflight = []   # the copies of every submitted member are complete: their buffers may go
 
     def solution(self, out=None):
         if out is None:
@@ -287,6 +288,8 @@ class TimeSolverExplicitRK4:
             assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.num_owned_cells * 5
             return a.ctypes.data
         _abi.check(self._lib.ma_solver_submit(self._handle, ptr(state_in), ptr(state_out), nsteps))
+        # the copies run after this call returns: keep the arrays alive until synchronize()
+        self._inflight = getattr(self, "_inflight", []) + [(state_in, state_out)]
 
     def field(self, which):
         shape = {FIELD_GRADIENT: (self.num_owned_cells, 5, 3), FIELD_LIMITER: (self.num_owned_cells, 5),
