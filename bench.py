@@ -530,10 +530,19 @@ def gpu_arm(args):
         elif key in tj:
             traffic_note = "profiles/traffic.json was captured on other kernel sources (hash %s, now %s): not quoted" % (
                 tj.get("source_hash"), source_hash())
+    # FP64 pipe utilisation of the stage kernels: an ncu metric, quoted from the committed --set full capture of the
+    # same kernel sources (profiles/pipes.json), never measured under the timed region
+    fp64_pipe = None
+    pp = os.path.join(ROOT, "profiles", "pipes.json")
+    if second and optd["viscous"] and os.path.isfile(pp):
+        with open(pp) as f:
+            pj = json.load(f)
+        if pj.get("source_hash") == source_hash():
+            fp64_pipe = {"pct": pj.get("fp64_pipe_pct"), "source": pj.get("source")}
     bpcu = BYTES_PER_CELL_UPDATE_O2 if (second or optd["viscous"]) else BYTES_PER_CELL_UPDATE_O1
     roofline = {"bound": "hbm", "kernel": "flux_rk_tma_kernel (face fluxes + slot-ordered gather + RK stage update; launched once per pass of the shared-cut-face scheme, the time is the stage's launches together)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": flux_bytes, "launch_ms": flux_ms,
+                "algorithmic_bytes_per_launch": flux_bytes, "launch_ms": flux_ms, "fp64_pipe": fp64_pipe,
                 "share_of_step": t["flux_seconds"] / t["step_seconds"],
                 "flux_evaluations_per_cell": t["faces_evaluated"] / float(n_owned),
                 "flux_evaluations_per_cell_unshared": t["tile_faces_total"] / float(n_owned),

@@ -63,6 +63,11 @@ def test_traffic_is_quoted_only_for_the_sources_it_was_measured_on():
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
         tj = json.load(f)
     assert len(bench.source_hash()) == 16 and "source_hash" in tj and tj["flux_rk_o2"]["dram_bytes_per_cell"] > 0
+    # the committed captures belong to the committed kernels: both figures are quoted by the next bench run
+    assert tj["source_hash"] == bench.source_hash()
+    with open(os.path.join(ROOT, "profiles", "pipes.json")) as f:
+        pj = json.load(f)
+    assert pj["source_hash"] == bench.source_hash() and all(0 < v < 100 for v in pj["fp64_pipe_pct"].values())
 
 
 def test_gpu_arm_fails_loudly_without_a_gpu():
