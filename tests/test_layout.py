@@ -36,6 +36,22 @@ def test_layout_invariants(checker, args):
 
 
 @pytest.mark.parametrize("share", ["", "1"])
+@pytest.mark.parametrize("args", [(37, 21, 13), (16, 9, 7, 3, 5, 2), (5, 3, 2, 8, 8, 8)])
+def test_layout_does_not_depend_on_the_order_of_the_face_list(checker, args, share):
+    """The reference's mesh generator hands over its internal faces in a random order (Parallel3DMesh.h:362, an unseeded
+    std::random_shuffle): the device layout is a function of the cells' connectivity, not of where a face sits in the
+    caller's list — same bytes for the creation order and for two shuffles of it."""
+    sums = set()
+    for seed in (None, "1", "2"):
+        env = {"MINIAERO_CHECK_SHARE": "1"} if share else {}
+        if seed:
+            env["MINIAERO_CHECK_SHUFFLE"] = seed
+        out = _run(checker, args, env)
+        sums.add(re.search(r"layout checksum: ([0-9a-f]{16})", out).group(1))
+    assert len(sums) == 1, sums
+
+
+@pytest.mark.parametrize("share", ["", "1"])
 @pytest.mark.parametrize("args", [(37, 21, 13), (64, 32, 32), (16, 9, 7, 3, 5, 2)])
 def test_layout_does_not_depend_on_the_thread_count(checker, args, share):
     """The host builder runs its O(cells) loops in parallel, first-touches its arrays from all threads and shares face

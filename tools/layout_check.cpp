@@ -3,6 +3,7 @@
 // per distinct double-word modulo 16 ... the model of DESIGN.md §3).
 //   g++ -O2 -std=c++17 -fopenmp -Iinclude -Iminiaero_b200/csrc tools/layout_check.cpp miniaero_b200/build/{layout,host_mesh,host_common}.o -o /tmp/layout_check
 //   /tmp/layout_check NX NY NZ [tx ty tz] [threads]
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +34,37 @@ int main(int argc, char **argv) {
   ma_mesh_storage *mh = nullptr;
   if (ma_mesh_generate(&opt, 0, 1, &mh)) return printf("mesh: %s\n", ma_last_error()), 1;
   const ma_mesh *mesh = ma_mesh_view(mh);
+  // MINIAERO_CHECK_SHUFFLE=seed: hand the builder the internal faces in a random order, as the reference's mesh
+  // generator does (Parallel3DMesh.h:362 shuffles them, unseeded): the layout must not depend on it
+  ma_mesh shuffled;
+  std::vector<double> sx, sn, st, sb;
+  std::vector<int> sc, sf;
+  if (const char *seed = getenv("MINIAERO_CHECK_SHUFFLE")) {
+    const ma_faces &F = mesh->internal_faces;
+    std::vector<int> perm(F.nfaces);
+    for (int i = 0; i < F.nfaces; ++i) perm[i] = i;
+    unsigned long long r = 88172645463325252ULL + (unsigned long long)atoll(seed);
+    for (int i = F.nfaces - 1; i > 0; --i) {  // Fisher-Yates on xorshift64
+      r ^= r << 13, r ^= r >> 7, r ^= r << 17;
+      std::swap(perm[i], perm[r % (unsigned long long)(i + 1)]);
+    }
+    sx.resize(3 * (size_t)F.nfaces), sn.resize(sx.size()), st.resize(sx.size()), sb.resize(sx.size());
+    sc.resize(2 * (size_t)F.nfaces), sf.resize(sc.size());
+    for (int i = 0; i < F.nfaces; ++i) {
+      const size_t j = (size_t)perm[i];
+      for (int d = 0; d < 3; ++d) {
+        sx[3 * (size_t)i + d] = F.coordinates[3 * j + d], sn[3 * (size_t)i + d] = F.face_normal[3 * j + d];
+        st[3 * (size_t)i + d] = F.face_tangent[3 * j + d], sb[3 * (size_t)i + d] = F.face_binormal[3 * j + d];
+      }
+      for (int d = 0; d < 2; ++d)
+        sc[2 * (size_t)i + d] = F.face_cell_conn[2 * j + d], sf[2 * (size_t)i + d] = F.cell_flux_index[2 * j + d];
+    }
+    shuffled = *mesh;
+    shuffled.internal_faces.coordinates = sx.data(), shuffled.internal_faces.face_normal = sn.data();
+    shuffled.internal_faces.face_tangent = st.data(), shuffled.internal_faces.face_binormal = sb.data();
+    shuffled.internal_faces.face_cell_conn = sc.data(), shuffled.internal_faces.cell_flux_index = sf.data();
+    mesh = &shuffled;
+  }
   ma::HostLayout L;
   const auto t0 = std::chrono::steady_clock::now();
   const bool share = getenv("MINIAERO_CHECK_SHARE") != nullptr;  // shared cut faces (layout.h)
