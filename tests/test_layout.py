@@ -51,6 +51,17 @@ def test_layout_does_not_depend_on_the_order_of_the_face_list(checker, args, sha
     assert len(sums) == 1, sums
 
 
+@pytest.mark.parametrize("how,message", [("conn", "out of range"), ("slot", "out of range"),
+                                         ("missing", "2 (cell, slot) pairs of owned cells have no face"),
+                                         ("duplicate", "2 (cell, slot) pairs of owned cells have no face")])
+def test_malformed_meshes_are_refused(checker, how, message):
+    """ma_solver_create's mesh checks (layout.cpp, ArrayAccess): a face naming a cell that does not exist, a slot
+    outside 0..5, a hex cell with fewer than six faces — each is an error with a text, not a crash or a wrong layout."""
+    p = subprocess.run([checker, "9", "7", "5"], capture_output=True, text=True,
+                       env=dict(os.environ, MINIAERO_CHECK_CORRUPT=how))
+    assert p.returncode == 1 and p.stdout.startswith("layout: mesh: ") and message in p.stdout, p.stdout + p.stderr
+
+
 @pytest.mark.parametrize("share", ["", "1"])
 @pytest.mark.parametrize("args", [(37, 21, 13), (64, 32, 32), (16, 9, 7, 3, 5, 2)])
 def test_layout_does_not_depend_on_the_thread_count(checker, args, share):

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -39,6 +40,8 @@ int main(int argc, char **argv) {
   ma_mesh shuffled;
   std::vector<double> sx, sn, st, sb;
   std::vector<int> sc, sf;
+  const char *corrupt = getenv("MINIAERO_CHECK_CORRUPT");  // conn | slot | missing | duplicate: a malformed mesh must be refused
+  if (corrupt && !getenv("MINIAERO_CHECK_SHUFFLE")) setenv("MINIAERO_CHECK_SHUFFLE", "0", 1);  // work on the copies below
   if (const char *seed = getenv("MINIAERO_CHECK_SHUFFLE")) {
     const ma_faces &F = mesh->internal_faces;
     std::vector<int> perm(F.nfaces);
@@ -63,6 +66,16 @@ int main(int argc, char **argv) {
     shuffled.internal_faces.coordinates = sx.data(), shuffled.internal_faces.face_normal = sn.data();
     shuffled.internal_faces.face_tangent = st.data(), shuffled.internal_faces.face_binormal = sb.data();
     shuffled.internal_faces.face_cell_conn = sc.data(), shuffled.internal_faces.cell_flux_index = sf.data();
+    if (corrupt && F.nfaces > 2) {
+      const std::string how = corrupt;
+      const size_t f = (size_t)F.nfaces / 2;
+      if (how == "conn") sc[2 * f + 1] = mesh->num_owned_cells + mesh->num_ghosts + 5;  // a cell that does not exist
+      if (how == "slot") sf[2 * f] = 6;                                                 // hex cells have slots 0..5
+      if (how == "missing") shuffled.internal_faces.nfaces = F.nfaces - 1;             // two (cell, slot) pairs lose their face
+      if (how == "duplicate") {                                                         // one face listed twice, another not at all
+        for (int d = 0; d < 2; ++d) sc[2 * f + d] = sc[2 * (f - 1) + d], sf[2 * f + d] = sf[2 * (f - 1) + d];
+      }
+    }
     mesh = &shuffled;
   }
   ma::HostLayout L;
